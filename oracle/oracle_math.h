@@ -1,0 +1,214 @@
+/*
+ * oracle_math.h -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * Stand-ins for the OpenCL C builtins that /root/reference/src/render.cl calls
+ * (log :152, cos :153, sqrt :152/:195/:444/:453/:531, pow :383, pown :177,
+ * atan2pi :390, normalize :157/:343/:421/:461/:516, sign :162/:462, mix :427/:432/:436,
+ * min/max :285-286/:383/:443, clamp :480, dot/cross everywhere).
+ *
+ * The OpenCL builtins are third-party arithmetic that is NOT under /root/reference: they are
+ * supplied by whichever OpenCL driver JIT-compiles render.cl ("default device",
+ * src/tracer.cpp:13; no driver or version is pinned by the reference, and no OpenCL runtime
+ * exists in this image).  PARITY UNPINNED at this boundary: the definitions below are this
+ * repository's documented choices.  Every function is built only from IEEE-754 correctly
+ * rounded operations (+ - * / sqrt fma, int<->float conversions), so a CPU compiled with
+ * -ffp-contract=off and a GPU compiled with --fmad=false produce the same bits.
+ * Polynomials are the published Cephes single-precision kernels (S. Moshier, cephes/single:
+ * logf.c, sinf.c, atanf.c).  Every fused multiply-add is spelled fmaf()/fma() explicitly;
+ * nothing else may be contracted.
+ */
+#ifndef ORACLE_MATH_H
+#define ORACLE_MATH_H
+
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+typedef struct { float x, y, z; } v3;
+
+static inline uint32_t om_f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+static inline float om_u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+static inline uint64_t om_d2u(double f) { uint64_t u; memcpy(&u, &f, 8); return u; }
+static inline double om_u2d(uint64_t u) { double f; memcpy(&f, &u, 8); return f; }
+
+static inline float om_fma(float a, float b, float c) { return __builtin_fmaf(a, b, c); }
+static inline float om_sqrt(float a) { return __builtin_sqrtf(a); }
+
+/* OpenCL fmin/fmax on NaN are left open by the slab test (render.cl:285-286); we pin them as
+ * plain comparisons (SURVEY hazard vii). */
+static inline float om_min(float a, float b) { return b < a ? b : a; }
+static inline float om_max(float a, float b) { return a < b ? b : a; }
+
+/* OpenCL sign(): +-1, +-0 kept, NaN -> 0 (render.cl:162, :462). */
+static inline float om_sign(float x) {
+	if (x > 0.0f) return 1.0f;
+	if (x < 0.0f) return -1.0f;
+	if (x == x) return x;
+	return 0.0f;
+}
+
+/* mix(x,y,a) = x + (y-x)*a, fused (render.cl:427,:432,:436). */
+static inline float om_mix(float x, float y, float a) { return om_fma(y - x, a, x); }
+
+static inline v3 v3_make(float x, float y, float z) { v3 r = {x, y, z}; return r; }
+static inline v3 v3_add(v3 a, v3 b) { return v3_make(a.x + b.x, a.y + b.y, a.z + b.z); }
+static inline v3 v3_sub(v3 a, v3 b) { return v3_make(a.x - b.x, a.y - b.y, a.z - b.z); }
+static inline v3 v3_mul(v3 a, v3 b) { return v3_make(a.x * b.x, a.y * b.y, a.z * b.z); }
+static inline v3 v3_scale(v3 a, float s) { return v3_make(a.x * s, a.y * s, a.z * s); }
+static inline v3 v3_neg(v3 a) { return v3_make(-a.x, -a.y, -a.z); }
+/* a*s + b, fused per component */
+static inline v3 v3_fma(v3 a, float s, v3 b) {
+	return v3_make(om_fma(a.x, s, b.x), om_fma(a.y, s, b.y), om_fma(a.z, s, b.z));
+}
+/* dot = fma(z,z', fma(y,y', x*x')) */
+static inline float v3_dot(v3 a, v3 b) { return om_fma(a.z, b.z, om_fma(a.y, b.y, a.x * b.x)); }
+/* cross component = fma(a1,b2, -(a2*b1)) */
+static inline v3 v3_cross(v3 a, v3 b) {
+	return v3_make(om_fma(a.y, b.z, -(a.z * b.y)), om_fma(a.z, b.x, -(a.x * b.z)),
+	               om_fma(a.x, b.y, -(a.y * b.x)));
+}
+/* normalize(v) = v * (1 / sqrt(dot(v,v))); no special-casing of 0 / inf (hazard iii) */
+static inline v3 v3_normalize(v3 a) {
+	float inv = 1.0f / om_sqrt(v3_dot(a, a));
+	return v3_scale(a, inv);
+}
+static inline v3 v3_mix(v3 a, v3 b, float t) {
+	return v3_make(om_mix(a.x, b.x, t), om_mix(a.y, b.y, t), om_mix(a.z, b.z, t));
+}
+
+/* natural log for x == 0 or normal positive x (the only inputs render.cl:152 can produce:
+ * u = r * 2^-32).  Cephes logf.c kernel. */
+static inline float om_log(float x) {
+	if (x == 0.0f) return -INFINITY;
+	uint32_t ix = om_f2u(x);
+	int e = (int)(ix >> 23) - 127;
+	float m = om_u2f((ix & 0x007fffffu) | 0x3f800000u); /* [1,2) */
+	if (m > 1.41421356237f) { m = m * 0.5f; e += 1; }
+	float f = m - 1.0f;
+	float z = f * f;
+	float p = 7.0376836292E-2f;
+	p = om_fma(p, f, -1.1514610310E-1f);
+	p = om_fma(p, f, 1.1676998740E-1f);
+	p = om_fma(p, f, -1.2420140846E-1f);
+	p = om_fma(p, f, 1.4249322787E-1f);
+	p = om_fma(p, f, -1.6668057665E-1f);
+	p = om_fma(p, f, 2.0000714765E-1f);
+	p = om_fma(p, f, -2.4999993993E-1f);
+	p = om_fma(p, f, 3.3333331174E-1f);
+	float y = (f * z) * p;
+	float fe = (float)e;
+	y = om_fma(fe, -2.12194440e-4f, y);
+	y = om_fma(-0.5f, z, y);
+	float r = f + y;
+	r = om_fma(fe, 0.693359375f, r);
+	return r;
+}
+
+/* cos for |x| <= 8192 (render.cl:153 only passes theta in [0, 2*pi]).  Cephes sinf.c/cosf. */
+static inline float om_cos(float x) {
+	x = __builtin_fabsf(x);
+	int j = (int)(1.27323954473516f * x);
+	j = (j + 1) & ~1;
+	float y = (float)j;
+	x = om_fma(-y, 0.78515625f, x);
+	x = om_fma(-y, 2.4187564849853515625e-4f, x);
+	x = om_fma(-y, 3.77489497744594108e-8f, x);
+	float z = x * x;
+	int q = j & 7; /* 0,2,4,6 */
+	float r;
+	if (q == 2 || q == 6) {
+		float p = -1.9515295891E-4f;
+		p = om_fma(p, z, 8.3321608736E-3f);
+		p = om_fma(p, z, -1.6666654611E-1f);
+		r = om_fma(p * z, x, x);
+	} else {
+		float p = 2.443315711809948E-005f;
+		p = om_fma(p, z, -1.388731625493765E-003f);
+		p = om_fma(p, z, 4.166664568298827E-002f);
+		r = om_fma(p * z, z, om_fma(-0.5f, z, 1.0f));
+	}
+	/* cos(x0) with x0 = x + q*pi/4:  q=0: cos x, q=2: -sin x, q=4: -cos x, q=6: sin x */
+	if (q == 2 || q == 4) r = -r;
+	return r;
+}
+
+/* atan for any finite x.  Cephes atanf.c. */
+static inline float om_atan(float x0) {
+	float x = __builtin_fabsf(x0);
+	float y;
+	if (x > 2.414213562373095f) { y = 1.5707963267948966192f; x = -(1.0f / x); }
+	else if (x > 0.4142135623730950f) { y = 0.7853981633974483096f; x = (x - 1.0f) / (x + 1.0f); }
+	else y = 0.0f;
+	float z = x * x;
+	float p = 8.05374449538e-2f;
+	p = om_fma(p, z, -1.38776856032E-1f);
+	p = om_fma(p, z, 1.99777106478E-1f);
+	p = om_fma(p, z, -3.33329491539E-1f);
+	y = y + om_fma(p * z, x, x);
+	return x0 < 0.0f ? -y : y;
+}
+
+/* atan2pi(y,x) = atan2(y,x)/pi (render.cl:390); result in [-1,1]. */
+static inline float om_atan2pi(float y, float x) {
+	if (x == 0.0f) {
+		if (y == 0.0f) return 0.0f;
+		return y > 0.0f ? 0.5f : -0.5f;
+	}
+	float a = om_atan(y / x);
+	if (x < 0.0f) a = a + (y < 0.0f ? -3.14159265358979323846f : 3.14159265358979323846f);
+	return a * 0.31830988618379067154f;
+}
+
+/* pow(x,y) for x in [0, +inf) and finite y (render.cl:383: x = max(dot,0), y = sun_focus).
+ * Evaluated as exp(y*log x) in double with Taylor kernels, rounded once to float. */
+static inline double om_log_d(double x) { /* x normal positive */
+	uint64_t ix = om_d2u(x);
+	int e = (int)(ix >> 52) - 1023;
+	double m = om_u2d((ix & 0x000fffffffffffffull) | 0x3ff0000000000000ull);
+	if (m > 1.4142135623730951) { m = m * 0.5; e += 1; }
+	double s = (m - 1.0) / (m + 1.0);
+	double s2 = s * s;
+	double p = 1.0 / 19.0;
+	p = __builtin_fma(p, s2, 1.0 / 17.0);
+	p = __builtin_fma(p, s2, 1.0 / 15.0);
+	p = __builtin_fma(p, s2, 1.0 / 13.0);
+	p = __builtin_fma(p, s2, 1.0 / 11.0);
+	p = __builtin_fma(p, s2, 1.0 / 9.0);
+	p = __builtin_fma(p, s2, 1.0 / 7.0);
+	p = __builtin_fma(p, s2, 1.0 / 5.0);
+	p = __builtin_fma(p, s2, 1.0 / 3.0);
+	p = __builtin_fma(p, s2, 1.0);
+	return __builtin_fma((double)e, 0.6931471805599453094, (2.0 * s) * p);
+}
+static inline double om_exp_d(double z) { /* |z| < 700 */
+	double k = __builtin_rint(z * 1.4426950408889634074);
+	double r = __builtin_fma(-k, 6.93147180369123816490e-01, z);
+	r = __builtin_fma(-k, 1.90821492927058770002e-10, r);
+	double p = 1.0 / 6227020800.0; /* 1/13! */
+	p = __builtin_fma(p, r, 1.0 / 479001600.0);
+	p = __builtin_fma(p, r, 1.0 / 39916800.0);
+	p = __builtin_fma(p, r, 1.0 / 3628800.0);
+	p = __builtin_fma(p, r, 1.0 / 362880.0);
+	p = __builtin_fma(p, r, 1.0 / 40320.0);
+	p = __builtin_fma(p, r, 1.0 / 5040.0);
+	p = __builtin_fma(p, r, 1.0 / 720.0);
+	p = __builtin_fma(p, r, 1.0 / 120.0);
+	p = __builtin_fma(p, r, 1.0 / 24.0);
+	p = __builtin_fma(p, r, 1.0 / 6.0);
+	p = __builtin_fma(p, r, 0.5);
+	p = __builtin_fma(p, r, 1.0);
+	p = __builtin_fma(p, r, 1.0);
+	int64_t ki = (int64_t)k;
+	return p * om_u2d((uint64_t)(ki + 1023) << 52);
+}
+static inline float om_pow(float x, float y) {
+	if (y == 0.0f) return 1.0f;
+	if (x == 0.0f) return y > 0.0f ? 0.0f : INFINITY;
+	if (x == 1.0f) return 1.0f;
+	double z = (double)y * om_log_d((double)x);
+	if (z < -104.0) return 0.0f;
+	if (z > 89.0) return INFINITY;
+	return (float)om_exp_d(z);
+}
+
+#endif

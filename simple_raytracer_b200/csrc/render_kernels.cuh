@@ -1,0 +1,531 @@
+// render_kernels.cuh -- the path-tracing hot path for sm_100a.
+//
+// Replaces the OpenCL kernels `render` and `average` of reference src/render.cl:483-535 (and every
+// helper they call, :114-481).  This is not a translation of that file: the device data is SoA with
+// model triangles pre-transformed to world space (v0, e1, e2) at upload, path state lives in
+// registers, and the bounce loop is FLATTENED -- one persistent thread owns a stream of
+// (pixel, sample) paths and runs exactly one bounce per loop trip, regenerating the next camera
+// path in place the moment its current path ends.  A warp therefore never waits on its longest path:
+// terminated lanes are refilled through a ballot-aggregated atomic on a global pixel cursor, and
+// warps stay full until the frame runs dry.  Per-pixel sample order (render.cl:495-520) is kept
+// because a lane owns all num_samples paths of its pixel, so results are bit-identical to the
+// sequential formulation.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "device_math.cuh"
+
+namespace srt {
+
+enum { SHAPE_SPHERE = 0, SHAPE_PLANE = 1, SHAPE_MODEL = 2 };
+
+// Device scene: SoA primitive buffers (see DESIGN.md "Data layout in HBM").
+struct DevScene {
+	int num_shapes;
+	int has_models;
+	const int4 *shape_hdr;    // {type, material, soa_tri_begin, tri_count} in reference array order
+	const float4 *shape_a;    // sphere {c.xyz, r} | plane {p0.xyz, -} | model {bmin.xyz, -}
+	const float4 *shape_b;    // sphere {-}        | plane {n.xyz, -}  | model {bmax.xyz, -}
+	const float4 *tri_v0;     // world-space v0           (hot, 16 B each)
+	const float4 *tri_e1;     // world-space v1 - v0      (hot)
+	const float4 *tri_e2;     // world-space v2 - v0      (hot)
+	const float4 *tri_n;      // 3 per triangle: object-space vertex normals (cold: winner only)
+	const float4 *model_xf;   // 4 per shape slot: model matrix columns      (cold)
+	const float4 *materials;  // 4 per material: the reference's 64-byte record as 4 x float4
+	const float4 *sky;        // RGBA f32 texels, row 0 = v 0
+	int sky_w, sky_h;
+	float sun_focus, sun_intensity;
+	float sun_color[3];
+	float sun_dir[3];
+};
+
+struct RenderParams {
+	int width, height, num_samples, num_bounces;
+	float aspect_ratio, fov_scale;
+	int show_normals;
+	float c2w[16];  // column-major
+	uint32_t time;
+	// row-band tiling (srt_set_row_bands)
+	int band_h, band_i, band_n;
+	int my_rows;            // number of rows this launch renders
+	unsigned int total_items;  // my_rows * width
+};
+
+struct Counters {
+	unsigned long long samples, bounces, tri_tests, aabb_pass, hits, sky;
+};
+
+struct Hit {
+	float t;
+	int shape;  // index into the shape list, -1 = miss
+	int tri;    // SoA triangle index of the winning triangle (models)
+};
+
+// ---- closest hit -----------------------------------------------------------------------------
+// reference closest_intersection, render.cl:293-378.  Shapes are visited in array order and a hit
+// replaces the current one only if strictly closer (:306,:332,:356), so the lowest index wins ties.
+// Normal / position of the winner are reconstructed afterwards (finish_hit) instead of at every
+// improvement; only the last improvement is observable.
+template <bool COUNT>
+__device__ __forceinline__ Hit closest_hit(const DevScene &sc, vec3 o, vec3 d, Counters &cnt) {
+	Hit hit;
+	hit.t = __int_as_float(0x7f800000);
+	hit.shape = -1;
+	hit.tri = -1;
+	vec3 inv = mk(0.f, 0.f, 0.f);
+	if (sc.has_models) inv = mk(div_(1.0f, d.x), div_(1.0f, d.y), div_(1.0f, d.z));  // :297
+
+	for (int i = 0; i < sc.num_shapes; ++i) {
+		const int4 hdr = __ldg(&sc.shape_hdr[i]);
+		const float4 a = __ldg(&sc.shape_a[i]);
+		if (hdr.x == SHAPE_SPHERE) {
+			// intersect_sphere, :180-204
+			vec3 L = xyz(a) - o;
+			float b = dot(L, d);
+			float c = fma_(-a.w, a.w, dot(L, L));
+			float disc = fma_(b, b, -c);
+			if (disc >= 0.0f) {
+				float sq = sqrt_(disc);
+				float t = b - sq;
+				if (t < 0.0f) t = b + sq;
+				if (t >= 0.0f && t < hit.t) {
+					hit.t = t;
+					hit.shape = i;
+				}
+			}
+		} else if (hdr.x == SHAPE_PLANE) {
+			// intersect_plane, :206-221
+			const float4 nb = __ldg(&sc.shape_b[i]);
+			vec3 n = xyz(nb);
+			float denom = dot(n, d);
+			if (fabsf(denom) != 0.0f) {
+				float t = div_(dot(n, xyz(a) - o), denom);
+				if (t >= 0.0f && t < hit.t) {
+					hit.t = t;
+					hit.shape = i;
+				}
+			}
+		} else if (hdr.x == SHAPE_MODEL) {
+			// intersection_aabb, :279-290, with tmax = current closest t (:319)
+			const float4 bb = __ldg(&sc.shape_b[i]);
+			float tmin = 0.0f, tmax = hit.t;
+			{
+				float t1 = (a.x - o.x) * inv.x, t2 = (bb.x - o.x) * inv.x;
+				tmin = max_(tmin, min_(t1, t2));
+				tmax = min_(tmax, max_(t1, t2));
+				t1 = (a.y - o.y) * inv.y, t2 = (bb.y - o.y) * inv.y;
+				tmin = max_(tmin, min_(t1, t2));
+				tmax = min_(tmax, max_(t1, t2));
+				t1 = (a.z - o.z) * inv.z, t2 = (bb.z - o.z) * inv.z;
+				tmin = max_(tmin, min_(t1, t2));
+				tmax = min_(tmax, max_(t1, t2));
+			}
+			const bool pass = tmin < tmax;
+			if (COUNT && pass) {
+				cnt.aabb_pass += 1;
+				cnt.tri_tests += (unsigned)hdr.w;
+			}
+			if (pass) {
+				// brute-force triangle loop, :324-350, on pre-transformed (v0, e1, e2).
+				// Moller-Trumbore (:243-275) with a division-free conservative reject placed
+				// before the exact test: a triangle is dropped early only when the exact test
+				// is certain to fail its `u` range check (proof in DESIGN.md "Triangle filter").
+				const int begin = hdr.z, count = hdr.w;
+#pragma unroll 2
+				for (int k = 0; k < count; ++k) {
+					const float4 v0 = __ldg(&sc.tri_v0[begin + k]);
+					const float4 e1 = __ldg(&sc.tri_e1[begin + k]);
+					const float4 e2 = __ldg(&sc.tri_e2[begin + k]);
+					vec3 h = cross(d, xyz(e2));
+					float det = dot(xyz(e1), h);
+					vec3 s = o - xyz(v0);
+					float su = dot(s, h);
+					// certain u > 1:  |su| > |det|*(1+1e-6) with equal signs
+					// certain u < 0:  opposite signs and |su| large enough not to underflow
+					float ad = fabsf(det), as = fabsf(su);
+					bool opposite = (__float_as_int(det) ^ __float_as_int(su)) < 0;
+					bool reject = opposite ? (as > 1e-6f) : (as > ad * 1.000001f);
+					if (reject || det == 0.0f) continue;
+					float f = div_(1.0f, det);
+					float u = f * su;
+					if (u < 0.0f || u > 1.0f) continue;
+					vec3 q = cross(s, xyz(e1));
+					float v = f * dot(d, q);
+					if (v < 0.0f || u + v > 1.0f) continue;
+					float t = f * dot(xyz(e2), q);
+					if (t > 0.0f && t < hit.t) {
+						hit.t = t;
+						hit.shape = i;
+						hit.tri = begin + k;
+					}
+				}
+			}
+		}
+	}
+	return hit;
+}
+
+// Position and shading normal of the winning hit (render.cl:311-312, :337-343, :361-362) followed by
+// the front-face flip (:372-375).
+__device__ __forceinline__ void finish_hit(const DevScene &sc, const Hit &hit, vec3 o, vec3 d, vec3 &pos,
+                                           vec3 &n, bool &front, int &material) {
+	const int4 hdr = __ldg(&sc.shape_hdr[hit.shape]);
+	const float4 a = __ldg(&sc.shape_a[hit.shape]);
+	material = hdr.y;
+	pos = fma3(d, hit.t, o);
+	if (hdr.x == SHAPE_SPHERE) {
+		vec3 r = pos - xyz(a);
+		n = mk(div_(r.x, a.w), div_(r.y, a.w), div_(r.z, a.w));
+	} else if (hdr.x == SHAPE_PLANE) {
+		n = xyz(__ldg(&sc.shape_b[hit.shape]));
+	} else {
+		// barycentric_weights, :223-241 (weights come back rotated: (w2, w0, w1))
+		vec3 v0 = xyz(__ldg(&sc.tri_v0[hit.tri]));
+		vec3 e1 = xyz(__ldg(&sc.tri_e1[hit.tri]));
+		vec3 e2 = xyz(__ldg(&sc.tri_e2[hit.tri]));
+		vec3 v2 = pos - v0;
+		float d00 = dot(e1, e1), d01 = dot(e1, e2), d11 = dot(e2, e2);
+		float d20 = dot(v2, e1), d21 = dot(v2, e2);
+		float denom = fma_(d00, d11, -(d01 * d01));
+		float w0 = div_(fma_(d11, d20, -(d01 * d21)), denom);
+		float w1 = div_(fma_(d00, d21, -(d01 * d20)), denom);
+		float w2 = (1.0f - w0) - w1;
+		vec3 n0 = xyz(__ldg(&sc.tri_n[3 * hit.tri + 0]));
+		vec3 n1 = xyz(__ldg(&sc.tri_n[3 * hit.tri + 1]));
+		vec3 n2 = xyz(__ldg(&sc.tri_n[3 * hit.tri + 2]));
+		// n0*w2 + n1*w0 + n2*w1  (:341 with the rotated weights)
+		vec3 ns = mk(fma_(n2.x, w1, fma_(n1.x, w0, n0.x * w2)), fma_(n2.y, w1, fma_(n1.y, w0, n0.y * w2)),
+		             fma_(n2.z, w1, fma_(n1.z, w0, n0.z * w2)));
+		// transform_mat(model->transform, n, false), :342 (model matrix, w = 0)
+		const float4 m0 = __ldg(&sc.model_xf[4 * hit.shape + 0]);
+		const float4 m1 = __ldg(&sc.model_xf[4 * hit.shape + 1]);
+		const float4 m2 = __ldg(&sc.model_xf[4 * hit.shape + 2]);
+		const float4 m3 = __ldg(&sc.model_xf[4 * hit.shape + 3]);
+		vec3 nt = mk(fma_(m3.x, 0.0f, fma_(m2.x, ns.z, fma_(m1.x, ns.y, m0.x * ns.x))),
+		             fma_(m3.y, 0.0f, fma_(m2.y, ns.z, fma_(m1.y, ns.y, m0.y * ns.x))),
+		             fma_(m3.z, 0.0f, fma_(m2.z, ns.z, fma_(m1.z, ns.y, m0.z * ns.x))));
+		n = normalize(nt);
+	}
+	front = dot(n, d) < 0.0f;
+	if (!front) n = -n;
+}
+
+// sky_box, render.cl:380-394, with read_imagef(linear, clamp-to-edge, normalised) done as a manual
+// FP32 bilinear fetch (the texture unit's 9-bit weights would break parity with a CPU OpenCL device).
+__device__ __forceinline__ vec3 sky_box(const DevScene &sc, vec3 d) {
+	vec3 sun_dir = mk(sc.sun_dir[0], sc.sun_dir[1], sc.sun_dir[2]);
+	float sd = max_(dot(d, -sun_dir), 0.0f);
+	float pw = pow_(sd, sc.sun_focus);
+	vec3 sun = (mk(sc.sun_color[0], sc.sun_color[1], sc.sun_color[2]) * pw) * sc.sun_intensity;
+	float u = fma_(atan2pi_(d.z, d.x), 0.5f, 0.5f);
+	float v = fma_(d.y, 0.5f, 0.5f);
+	const int w = sc.sky_w, h = sc.sky_h;
+	float fu = fma_(u, (float)w, -0.5f), fv = fma_(v, (float)h, -0.5f);
+	float flu = floorf(fu), flv = floorf(fv);
+	float a = fu - flu, b = fv - flv;
+	int i0 = (int)flu, j0 = (int)flv;
+	int i1 = i0 + 1, j1 = j0 + 1;
+	i0 = min(max(i0, 0), w - 1);
+	i1 = min(max(i1, 0), w - 1);
+	j0 = min(max(j0, 0), h - 1);
+	j1 = min(max(j1, 0), h - 1);
+	const float4 t00 = __ldg(&sc.sky[(size_t)j0 * w + i0]);
+	const float4 t10 = __ldg(&sc.sky[(size_t)j0 * w + i1]);
+	const float4 t01 = __ldg(&sc.sky[(size_t)j1 * w + i0]);
+	const float4 t11 = __ldg(&sc.sky[(size_t)j1 * w + i1]);
+	float w00 = (1.0f - a) * (1.0f - b), w10 = a * (1.0f - b), w01 = (1.0f - a) * b, w11 = a * b;
+	vec3 tex = mk(fma_(w11, t11.x, fma_(w01, t01.x, fma_(w10, t10.x, w00 * t00.x))),
+	              fma_(w11, t11.y, fma_(w01, t01.y, fma_(w10, t10.y, w00 * t00.y))),
+	              fma_(w11, t11.z, fma_(w01, t01.z, fma_(w10, t10.z, w00 * t00.z))));
+	return tex + sun;
+}
+
+// camera ray for pixel (gx, gy), render.cl:496-516.  Returns the advanced seed in `seed`.
+__device__ __forceinline__ void camera_ray(const RenderParams &p, int gx, int gy, uint32_t &seed, vec3 &o,
+                                           vec3 &d) {
+	float u0 = random_float(seed);
+	float u1 = random_float(seed);
+	float ndc_x = div_((float)gx + u0, (float)p.width);
+	float ndc_y = div_((float)gy + u1, (float)p.height);
+	float sx = (fma_(2.0f, ndc_x, -1.0f) * p.aspect_ratio) * p.fov_scale;
+	float sy = fma_(-2.0f, ndc_y, 1.0f) * p.fov_scale;
+	const float *m = p.c2w;
+	o = mk(m[12], m[13], m[14]);
+	// matrix_by_vector(camera_to_world, (sx, sy, -1, 0)), :114-120
+	vec3 t = mk(fma_(m[12], 0.0f, fma_(m[8], -1.0f, fma_(m[4], sy, m[0] * sx))),
+	            fma_(m[13], 0.0f, fma_(m[9], -1.0f, fma_(m[5], sy, m[1] * sx))),
+	            fma_(m[14], 0.0f, fma_(m[10], -1.0f, fma_(m[6], sy, m[2] * sx))));
+	d = normalize(t);
+}
+
+// Scatter at a hit, render.cl:418-462.  Updates o, d, mask; consumes 9 or 10 random numbers.
+__device__ __forceinline__ void scatter(const DevScene &sc, int material, vec3 pos, vec3 n, bool front,
+                                        uint32_t &seed, vec3 &o, vec3 &d, vec3 &mask, float4 m0, float4 m1) {
+	o = pos;
+	// random_direction_hemisphere, :156-163
+	float gx = random_float_normal(seed);
+	float gy = random_float_normal(seed);
+	float gz = random_float_normal(seed);
+	vec3 rd = normalize(mk(gx, gy, gz));
+	rd = rd * sign_(dot(n, rd));
+	vec3 random_dir = normalize(n + rd);                       // :421
+	float k2 = 2.0f * dot(d, n);                                // reflect, :139-141
+	vec3 reflected = mk(fma_(-k2, n.x, d.x), fma_(-k2, n.y, d.y), fma_(-k2, n.z, d.z));
+	const bool is_metallic = m0.y > random_float(seed);         // :424
+	const bool is_specular = m0.z > random_float(seed);         // :425
+	vec3 rough = mix3(random_dir, reflected, m0.x);             // :427
+	const bool is_transparent = m1.x > random_float(seed);      // :429
+	vec3 nd;
+	if (!is_transparent) {
+		nd = mix3(random_dir, rough, (is_metallic || is_specular) ? 1.0f : 0.0f);  // :432
+		vec3 col = xyz(__ldg(&sc.materials[4 * material + 2]));
+		float sp = is_specular ? 1.0f : 0.0f;
+		mask = mask * mk(mix_(col.x, 1.0f, sp), mix_(col.y, 1.0f, sp), mix_(col.z, 1.0f, sp));  // :436
+	} else {
+		float ki = 2.0f * dot(rough, n);                        // in_dir = reflect(rough, n), :440
+		vec3 in_dir = mk(fma_(-ki, n.x, rough.x), fma_(-ki, n.y, rough.y), fma_(-ki, n.z, rough.z));
+		float mu = front ? div_(1.0f, m1.y) : m1.y;             // :442
+		float cos_theta = min_(1.0f, dot(in_dir, -n));          // :443
+		float sin_theta = sqrt_(fma_(-cos_theta, cos_theta, 1.0f));
+		bool reflected_t = mu * sin_theta > 1.0f;               // :446
+		if (!reflected_t) reflected_t = schlick_(mu, cos_theta) > random_float(seed);  // :447 (short-circuit)
+		if (reflected_t) {
+			nd = rough;                                         // :450
+		} else {
+			vec3 out_perp = fma3(n, cos_theta, in_dir) * mu;    // :452
+			float kp = -sqrt_(fabsf(1.0f - dot(out_perp, out_perp)));  // :453
+			nd = fma3(n, kp, out_perp);                         // :454
+			mask = mask * xyz(__ldg(&sc.materials[4 * material + 2]));  // :457
+		}
+	}
+	d = normalize(nd);                                          // :461
+	float sg = sign_(dot(n, d)) * 0.001f;                       // :462
+	o = fma3(n, sg, o);
+}
+
+// ---- kernel `render` ---------------------------------------------------------------------------
+constexpr int RENDER_THREADS = 256;
+
+template <bool COUNT>
+__global__ void __launch_bounds__(RENDER_THREADS, 2)
+render_kernel(const __grid_constant__ RenderParams p, const __grid_constant__ DevScene sc,
+              float4 *__restrict__ canvas, unsigned int *__restrict__ cursor, Counters *__restrict__ counters) {
+	const unsigned FULL = 0xffffffffu;
+	const int lane = threadIdx.x & 31;
+	Counters cnt = {0, 0, 0, 0, 0, 0};
+
+	bool alive = true;
+	int pix = -1, gx = 0, gy = 0;
+	int sample = p.num_samples;  // forces a pixel fetch on the first trip
+	int bounce = 0;
+	bool fresh = false;          // a camera ray must be generated
+	uint32_t seed = 0;
+	vec3 o = mk(0, 0, 0), d = mk(0, 0, 1), mask = mk(1, 1, 1), color = mk(0, 0, 0), pixsum = mk(0, 0, 0);
+	const float ns_f = (float)p.num_samples;
+
+	for (;;) {
+		// -- refill: lanes whose pixel is complete commit it and pull the next pixel id
+		const bool need_pixel = alive && sample == p.num_samples;
+		const unsigned need = __ballot_sync(FULL, need_pixel);
+		if (need) {
+			unsigned int base = 0;
+			if (lane == 0) base = atomicAdd(cursor, (unsigned int)__popc(need));
+			base = __shfl_sync(FULL, base, 0);
+			if (need_pixel) {
+				if (pix >= 0) {  // canvas[id] += color / num_samples, :520-522
+					float4 c = canvas[pix];
+					c.x += div_(pixsum.x, ns_f);
+					c.y += div_(pixsum.y, ns_f);
+					c.z += div_(pixsum.z, ns_f);
+					canvas[pix] = c;
+				}
+				const unsigned int item = base + __popc(need & ((1u << lane) - 1u));
+				if (item < p.total_items) {
+					int row = (int)(item / (unsigned)p.width);
+					gx = (int)(item - (unsigned)row * (unsigned)p.width);
+					gy = p.band_n > 1 ? ((row / p.band_h) * p.band_n + p.band_i) * p.band_h + (row % p.band_h) : row;
+					pix = gx + gy * p.width;
+					sample = 0;
+					pixsum = mk(0, 0, 0);
+					fresh = true;
+				} else {
+					alive = false;
+					pix = -1;
+				}
+			}
+		}
+		if (!__any_sync(FULL, alive)) break;
+		if (alive) {
+		if (fresh) {  // start path `sample` of pixel `pix`, :496-516
+			seed = ((uint32_t)sample + (uint32_t)pix * (uint32_t)p.num_samples) * p.time * 5304u;
+			camera_ray(p, gx, gy, seed, o, d);
+			mask = mk(1, 1, 1);
+			color = mk(0, 0, 0);
+			bounce = 0;
+			fresh = false;
+			if (COUNT) cnt.samples += 1;
+		}
+
+		// -- one bounce, :403-468
+		if (COUNT) cnt.bounces += 1;
+		const Hit hit = closest_hit<COUNT>(sc, o, d, cnt);
+		bool done;
+		if (hit.shape >= 0) {
+			if (COUNT) cnt.hits += 1;
+			vec3 pos, n;
+			bool front;
+			int material;
+			finish_hit(sc, hit, o, d, pos, n, front, material);
+			if (p.show_normals) {  // :407-410
+				color = mk(fma_(n.x, 0.5f, 0.5f), fma_(n.y, 0.5f, 0.5f), fma_(n.z, 0.5f, 0.5f));
+				done = true;
+			} else {
+				const float4 m0 = __ldg(&sc.materials[4 * material + 0]);
+				const float4 em = __ldg(&sc.materials[4 * material + 3]);
+				color = color + (mask * xyz(em)) * m0.w;  // :413
+				if (bounce == p.num_bounces - 1) {         // :415-416
+					done = true;
+				} else {
+					const float4 m1 = __ldg(&sc.materials[4 * material + 1]);
+					scatter(sc, material, pos, n, front, seed, o, d, mask, m0, m1);
+					bounce += 1;
+					done = false;
+				}
+			}
+		} else {  // :463-467
+			if (COUNT) cnt.sky += 1;
+			mask = mask * sky_box(sc, d);
+			color = color + mask;
+			done = true;
+		}
+		if (done) {
+			pixsum = pixsum + color;  // :518
+			sample += 1;
+			fresh = true;
+		}
+		}  // alive
+	}
+
+	if (COUNT) {
+		unsigned long long *c = reinterpret_cast<unsigned long long *>(&cnt);
+		for (int k = 0; k < 6; ++k) {
+			unsigned long long v = c[k];
+			for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(FULL, v, off);
+			if (lane == 0 && v) atomicAdd(reinterpret_cast<unsigned long long *>(counters) + k, v);
+		}
+	}
+}
+
+// ---- kernel `average`, render.cl:525-535 (aces :473-481) ---------------------------------------
+__device__ __forceinline__ float aces_sqrt(float x) {
+	const float a = 2.51f, b = 0.03f, c = 2.43f, dd = 0.59f, e = 0.14f;
+	float num = x * fma_(x, a, b);
+	float den = fma_(x, fma_(x, c, dd), e);
+	float r = div_(num, den);
+	r = r > 0.0f ? r : 0.0f;  // clamp; NaN -> 0
+	r = r < 1.0f ? r : 1.0f;
+	return sqrt_(r);
+}
+__global__ void __launch_bounds__(256)
+average_kernel(uint32_t num_steps, const float4 *__restrict__ canvas, uchar4 *__restrict__ output, int n) {
+	int id = blockIdx.x * blockDim.x + threadIdx.x;
+	if (id >= n) return;
+	const float steps = (float)num_steps;
+	float4 c = canvas[id];
+	float r = aces_sqrt(div_(c.x, steps)) * 255.0f;
+	float g = aces_sqrt(div_(c.y, steps)) * 255.0f;
+	float b = aces_sqrt(div_(c.z, steps)) * 255.0f;
+	// uchar4(255, r, g, b): A,R,G,B byte order, float -> uchar by truncation
+	output[id] = make_uchar4(255, (unsigned char)(int)r, (unsigned char)(int)g, (unsigned char)(int)b);
+}
+
+// ---- debug: primary hit of every pixel's sample-0 camera ray -----------------------------------
+__global__ void __launch_bounds__(256)
+primary_kernel(const __grid_constant__ RenderParams p, const __grid_constant__ DevScene sc,
+               int *__restrict__ shape_idx, float *__restrict__ t_out) {
+	int id = blockIdx.x * blockDim.x + threadIdx.x;
+	if (id >= p.width * p.height) return;
+	int gx = id % p.width, gy = id / p.width;
+	uint32_t seed = (0u + (uint32_t)id * (uint32_t)p.num_samples) * p.time * 5304u;
+	vec3 o, d;
+	camera_ray(p, gx, gy, seed, o, d);
+	Counters cnt = {0, 0, 0, 0, 0, 0};
+	Hit hit = closest_hit<false>(sc, o, d, cnt);
+	shape_idx[id] = hit.shape;
+	t_out[id] = hit.t;
+}
+
+// ---- scene upload: AoS Triangle[] -> pre-transformed SoA ---------------------------------------
+// One thread per (model instance, triangle).  Positions are transformed exactly as render.cl:326-328
+// does per ray (transform_mat(model->transform, pos, true), :114-120 operation order) and the edges
+// are the subtractions of :247-248, so every later intersection sees the same bits as the reference.
+struct ModelSpan {
+	int shape;      // shape slot (index into model_xf / 4)
+	int src_begin;  // first triangle in the AoS array (Model::triangle_index)
+	int dst_begin;  // first triangle in the SoA arrays
+	int count;
+};
+__global__ void __launch_bounds__(256)
+prepare_triangles_kernel(const float4 *__restrict__ aos /* 6 float4 per triangle */, const ModelSpan *__restrict__ spans,
+                         int n_spans, int total, const float4 *__restrict__ model_xf, float4 *__restrict__ v0_out,
+                         float4 *__restrict__ e1_out, float4 *__restrict__ e2_out, float4 *__restrict__ n_out) {
+	int g = blockIdx.x * blockDim.x + threadIdx.x;
+	if (g >= total) return;
+	int lo = 0, hi = n_spans - 1;  // last span with dst_begin <= g
+	while (lo < hi) {
+		int mid = (lo + hi + 1) >> 1;
+		if (spans[mid].dst_begin <= g) lo = mid;
+		else hi = mid - 1;
+	}
+	const ModelSpan sp = spans[lo];
+	const float4 *tri = aos + 6 * (size_t)(sp.src_begin + (g - sp.dst_begin));
+	const float4 m0 = model_xf[4 * sp.shape + 0], m1 = model_xf[4 * sp.shape + 1];
+	const float4 m2 = model_xf[4 * sp.shape + 2], m3 = model_xf[4 * sp.shape + 3];
+	vec3 w[3];
+	for (int j = 0; j < 3; ++j) {
+		const float4 pj = tri[2 * j + 1];
+		w[j] = mk(fma_(m3.x, 1.0f, fma_(m2.x, pj.z, fma_(m1.x, pj.y, m0.x * pj.x))),
+		          fma_(m3.y, 1.0f, fma_(m2.y, pj.z, fma_(m1.y, pj.y, m0.y * pj.x))),
+		          fma_(m3.z, 1.0f, fma_(m2.z, pj.z, fma_(m1.z, pj.y, m0.z * pj.x))));
+		n_out[3 * (size_t)g + j] = tri[2 * j];
+	}
+	vec3 e1 = w[1] - w[0], e2 = w[2] - w[0];
+	v0_out[g] = make_float4(w[0].x, w[0].y, w[0].z, 0.f);
+	e1_out[g] = make_float4(e1.x, e1.y, e1.z, 0.f);
+	e2_out[g] = make_float4(e2.x, e2.y, e2.z, 0.f);
+}
+
+// ---- device math self-test -------------------------------------------------------------------
+__global__ void math_kernel(int op, const float *__restrict__ x, const float *__restrict__ y, float *__restrict__ out,
+                            size_t n) {
+	size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	float r = 0.f;
+	switch (op) {
+	case 0: r = log_(x[i]); break;
+	case 1: r = cos_(x[i]); break;
+	case 2: r = atan2pi_(x[i], y[i]); break;
+	case 3: r = pow_(x[i], y[i]); break;
+	case 4: r = sqrt_(x[i]); break;
+	case 5: r = schlick_(x[i], y[i]); break;
+	}
+	out[i] = r;
+}
+
+// ---- FP32 FMA-chain micro-benchmark (the roofline denominator) ----------
+__global__ void __launch_bounds__(256) fma_peak_kernel(float *out, int iters, float a, float b) {
+	float r[16];
+#pragma unroll
+	for (int k = 0; k < 16; ++k) r[k] = (float)(threadIdx.x + k);
+	for (int i = 0; i < iters; ++i) {
+#pragma unroll
+		for (int k = 0; k < 16; ++k) r[k] = __fmaf_rn(r[k], a, b);
+	}
+	float s = 0.f;
+#pragma unroll
+	for (int k = 0; k < 16; ++k) s += r[k];
+	if (s == 123.456f) out[0] = s;
+}
+
+}  // namespace srt

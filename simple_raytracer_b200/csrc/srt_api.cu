@@ -1,0 +1,566 @@
+// srt_api.cu -- host side of the C ABI declared in include/srt.h.
+//
+// Replaces the boost.compute layer of reference src/tracer.cpp:1-116 (context / queue / buffers /
+// image / arg binding) with a CUDA stream, device buffers and the sm_100a kernels of
+// render_kernels.cuh.  No CPU fallback: every entry point either runs on the GPU or fails.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/srt.h"
+#include "render_kernels.cuh"
+
+static_assert(sizeof(srt_material) == 64 && offsetof(srt_material, color) == 32 && offsetof(srt_material, emission) == 48, "material");
+static_assert(sizeof(srt_sphere) == 32 && offsetof(srt_sphere, radius) == 16, "sphere");
+static_assert(sizeof(srt_plane) == 32 && offsetof(srt_plane, normal) == 16, "plane");
+static_assert(sizeof(srt_triangle) == 96, "triangle");
+static_assert(sizeof(srt_model) == 112 && offsetof(srt_model, bounding_min) == 16 && offsetof(srt_model, bounding_max) == 32 &&
+              offsetof(srt_model, transform) == 48, "model");
+static_assert(sizeof(srt_shape) == 128 && offsetof(srt_shape, shape) == 16, "shape");
+static_assert(sizeof(srt_render_data) == 112 && offsetof(srt_render_data, show_normals) == 24 &&
+              offsetof(srt_render_data, camera_to_world) == 32 && offsetof(srt_render_data, time) == 96 &&
+              offsetof(srt_render_data, tick) == 100, "render_data");
+static_assert(sizeof(srt_scene_data) == 96 && offsetof(srt_scene_data, horizon_color) == 16 &&
+              offsetof(srt_scene_data, sun_color) == 64 && offsetof(srt_scene_data, sun_direction) == 80, "scene_data");
+static_assert(sizeof(srt_counters) == sizeof(srt::Counters), "counters");
+
+namespace {
+
+std::string g_create_error;
+
+template <typename T>
+struct DevBuf {  // grow-only device buffer (rebuild_if_too_small, reference tracer.cpp:5-9)
+	T *ptr = nullptr;
+	size_t cap = 0;
+	cudaError_t reserve(size_t n) {
+		if (n <= cap) return cudaSuccess;
+		if (ptr) cudaFree(ptr);
+		ptr = nullptr;
+		cap = 0;
+		cudaError_t e = cudaMalloc(&ptr, std::max<size_t>(n, 1) * sizeof(T));
+		if (e == cudaSuccess) cap = n;
+		return e;
+	}
+	void release() {
+		if (ptr) cudaFree(ptr);
+		ptr = nullptr;
+		cap = 0;
+	}
+};
+
+}  // namespace
+
+struct srt_tracer {
+	int device = 0;
+	int width = 0, height = 0;
+	int sm_count = 0;
+	cudaStream_t stream = nullptr;
+	std::string error;
+
+	float4 *canvas = nullptr;  // float3 with 16-byte stride (tracer.cpp:39)
+	uchar4 *output = nullptr;  // ARGB8 (tracer.cpp:40)
+	uint8_t *pinned_out = nullptr;
+	float4 *sky = nullptr;
+	int sky_w = 0, sky_h = 0;
+	unsigned int *cursor = nullptr;
+	srt::Counters *counters = nullptr;
+
+	DevBuf<int4> shape_hdr;
+	DevBuf<float4> shape_a, shape_b, model_xf, materials;
+	DevBuf<float4> tri_aos, tri_v0, tri_e1, tri_e2, tri_n;
+	DevBuf<srt::ModelSpan> spans;
+	size_t n_shapes = 0, n_materials = 0, n_soa_tris = 0;
+	bool has_models = false;
+	srt_scene_data scene_data{};
+	bool have_scene = false;
+
+	int band_h = 1, band_i = 0, band_n = 1;
+	int render_grid = 0, render_grid_counted = 0;
+
+	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing;  // render launches since last query
+	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> event_pool;
+};
+
+namespace {
+
+int fail(srt_tracer *t, int code, const char *fmt, ...) {
+	char buf[512];
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(buf, sizeof buf, fmt, ap);
+	va_end(ap);
+	if (t) t->error = buf;
+	else g_create_error = buf;
+	return code;
+}
+
+#define SRT_CUDA(t, call)                                                                             \
+	do {                                                                                              \
+		cudaError_t e__ = (call);                                                                     \
+		if (e__ != cudaSuccess)                                                                       \
+			return fail((t), SRT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+	} while (0)
+
+#define SRT_BIND(t)                        \
+	do {                                   \
+		if (!(t)) return SRT_ERR_INVALID;  \
+		SRT_CUDA((t), cudaSetDevice((t)->device)); \
+	} while (0)
+
+srt::DevScene dev_scene(const srt_tracer *t) {
+	srt::DevScene s{};
+	s.num_shapes = (int)t->n_shapes;
+	s.has_models = t->has_models ? 1 : 0;
+	s.shape_hdr = t->shape_hdr.ptr;
+	s.shape_a = t->shape_a.ptr;
+	s.shape_b = t->shape_b.ptr;
+	s.tri_v0 = t->tri_v0.ptr;
+	s.tri_e1 = t->tri_e1.ptr;
+	s.tri_e2 = t->tri_e2.ptr;
+	s.tri_n = t->tri_n.ptr;
+	s.model_xf = t->model_xf.ptr;
+	s.materials = t->materials.ptr;
+	s.sky = t->sky;
+	s.sky_w = t->sky_w;
+	s.sky_h = t->sky_h;
+	const srt_scene_data &sd = t->scene_data;
+	s.sun_focus = sd.sun_focus;
+	s.sun_intensity = sd.sun_intensity;
+	s.sun_color[0] = sd.sun_color.x, s.sun_color[1] = sd.sun_color.y, s.sun_color[2] = sd.sun_color.z;
+	s.sun_dir[0] = sd.sun_direction.x, s.sun_dir[1] = sd.sun_direction.y, s.sun_dir[2] = sd.sun_direction.z;
+	return s;
+}
+
+int make_params(srt_tracer *t, const srt_render_data *rd, srt::RenderParams &p) {
+	if (!rd) return fail(t, SRT_ERR_INVALID, "render data is null");
+	if (rd->width != t->width || rd->height != t->height)
+		return fail(t, SRT_ERR_INVALID, "RenderData is %dx%d but the tracer was created %dx%d", rd->width, rd->height,
+		            t->width, t->height);
+	if (rd->num_samples < 1 || rd->num_bounces < 0)
+		return fail(t, SRT_ERR_INVALID, "num_samples must be >= 1 and num_bounces >= 0");
+	if (!t->have_scene) return fail(t, SRT_ERR_INVALID, "no scene uploaded");
+	p.width = rd->width;
+	p.height = rd->height;
+	p.num_samples = rd->num_samples;
+	p.num_bounces = rd->num_bounces;
+	p.aspect_ratio = rd->aspect_ratio;
+	p.fov_scale = rd->fov_scale;
+	p.show_normals = rd->show_normals ? 1 : 0;
+	memcpy(p.c2w, rd->camera_to_world, sizeof p.c2w);
+	p.time = rd->time;
+	p.band_h = t->band_h;
+	p.band_i = t->band_i;
+	p.band_n = t->band_n;
+	int rows = rd->height;
+	if (t->band_n > 1) {
+		rows = 0;
+		for (int y = 0; y < rd->height; ++y)
+			if ((y / t->band_h) % t->band_n == t->band_i) ++rows;
+	}
+	p.my_rows = rows;
+	p.total_items = (unsigned int)rows * (unsigned int)rd->width;
+	return SRT_OK;
+}
+
+template <bool COUNT>
+int launch_render(srt_tracer *t, const srt_render_data *rd) {
+	srt::RenderParams p{};
+	if (int rc = make_params(t, rd, p)) return rc;
+	int &grid = COUNT ? t->render_grid_counted : t->render_grid;
+	if (grid == 0) {
+		int per_sm = 0;
+		SRT_CUDA(t, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, srt::render_kernel<COUNT>, srt::RENDER_THREADS, 0));
+		grid = std::max(per_sm, 1) * t->sm_count;  // persistent: one full wave, work pulled from the cursor
+	}
+	SRT_CUDA(t, cudaMemsetAsync(t->cursor, 0, sizeof(unsigned int), t->stream));
+	std::pair<cudaEvent_t, cudaEvent_t> ev;
+	if (!t->event_pool.empty()) {
+		ev = t->event_pool.back();
+		t->event_pool.pop_back();
+	} else {
+		SRT_CUDA(t, cudaEventCreate(&ev.first));
+		SRT_CUDA(t, cudaEventCreate(&ev.second));
+	}
+	const srt::DevScene sc = dev_scene(t);
+	if (p.num_bounces == 0 || p.total_items == 0) {  // render.cl:403: zero bounces adds zero radiance
+		t->event_pool.push_back(ev);
+		return SRT_OK;
+	}
+	SRT_CUDA(t, cudaEventRecord(ev.first, t->stream));
+	srt::render_kernel<COUNT><<<grid, srt::RENDER_THREADS, 0, t->stream>>>(p, sc, t->canvas, t->cursor, t->counters);
+	SRT_CUDA(t, cudaEventRecord(ev.second, t->stream));
+	SRT_CUDA(t, cudaGetLastError());
+	t->timing.push_back(ev);
+	return SRT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int srt_abi_version(void) { return SRT_ABI_VERSION; }
+
+const char *srt_last_error(const srt_tracer *t) { return t ? t->error.c_str() : g_create_error.c_str(); }
+
+int srt_create(int width, int height, const float *skybox_rgba, int sky_w, int sky_h, int device, srt_tracer **out) {
+	if (!out) return fail(nullptr, SRT_ERR_INVALID, "out is null");
+	*out = nullptr;
+	if (width <= 0 || height <= 0 || (long long)width * height > 0x7fffffffLL)
+		return fail(nullptr, SRT_ERR_INVALID, "bad image size %dx%d", width, height);
+	if (!skybox_rgba || sky_w <= 0 || sky_h <= 0) return fail(nullptr, SRT_ERR_INVALID, "sky box is required (reference tracer.cpp:42-52)");
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+		cudaGetLastError();
+		return fail(nullptr, SRT_ERR_NO_DEVICE, "no CUDA device: this library has no CPU path");
+	}
+	if (device < 0) {
+		if (cudaGetDevice(&device) != cudaSuccess) device = 0;
+	}
+	if (device >= ndev) return fail(nullptr, SRT_ERR_INVALID, "device %d out of range (%d devices)", device, ndev);
+	srt_tracer *t = new (std::nothrow) srt_tracer();
+	if (!t) return fail(nullptr, SRT_ERR_INVALID, "out of host memory");
+	t->device = device;
+	t->width = width;
+	t->height = height;
+	t->sky_w = sky_w;
+	t->sky_h = sky_h;
+#define CREATE_CUDA(call)                                                                               \
+	do {                                                                                                \
+		cudaError_t e__ = (call);                                                                       \
+		if (e__ != cudaSuccess) {                                                                       \
+			fail(nullptr, SRT_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__));               \
+			srt_destroy(t);                                                                             \
+			return SRT_ERR_CUDA;                                                                        \
+		}                                                                                               \
+	} while (0)
+	CREATE_CUDA(cudaSetDevice(device));
+	cudaDeviceProp prop{};
+	CREATE_CUDA(cudaGetDeviceProperties(&prop, device));
+	t->sm_count = prop.multiProcessorCount;
+	CREATE_CUDA(cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking));
+	const size_t n = (size_t)width * height;
+	CREATE_CUDA(cudaMalloc(&t->canvas, n * sizeof(float4)));
+	CREATE_CUDA(cudaMalloc(&t->output, n * sizeof(uchar4)));
+	CREATE_CUDA(cudaMallocHost(&t->pinned_out, n * 4));
+	CREATE_CUDA(cudaMalloc(&t->cursor, sizeof(unsigned int)));
+	CREATE_CUDA(cudaMalloc(&t->counters, sizeof(srt::Counters)));
+	CREATE_CUDA(cudaMalloc(&t->sky, (size_t)sky_w * sky_h * sizeof(float4)));
+	CREATE_CUDA(cudaMemcpyAsync(t->sky, skybox_rgba, (size_t)sky_w * sky_h * sizeof(float4), cudaMemcpyHostToDevice, t->stream));
+	CREATE_CUDA(cudaMemsetAsync(t->canvas, 0, n * sizeof(float4), t->stream));
+	CREATE_CUDA(cudaMemsetAsync(t->counters, 0, sizeof(srt::Counters), t->stream));
+	CREATE_CUDA(cudaStreamSynchronize(t->stream));
+#undef CREATE_CUDA
+	*out = t;
+	return SRT_OK;
+}
+
+int srt_destroy(srt_tracer *t) {
+	if (!t) return SRT_OK;
+	cudaSetDevice(t->device);
+	if (t->stream) cudaStreamSynchronize(t->stream);
+	for (auto &e : t->timing) t->event_pool.push_back(e);
+	for (auto &e : t->event_pool) {
+		cudaEventDestroy(e.first);
+		cudaEventDestroy(e.second);
+	}
+	cudaFree(t->canvas);
+	cudaFree(t->output);
+	cudaFreeHost(t->pinned_out);
+	cudaFree(t->cursor);
+	cudaFree(t->counters);
+	cudaFree(t->sky);
+	t->shape_hdr.release(), t->shape_a.release(), t->shape_b.release(), t->model_xf.release(), t->materials.release();
+	t->tri_aos.release(), t->tri_v0.release(), t->tri_e1.release(), t->tri_e2.release(), t->tri_n.release(), t->spans.release();
+	if (t->stream) cudaStreamDestroy(t->stream);
+	delete t;
+	return SRT_OK;
+}
+
+int srt_upload_scene(srt_tracer *t, const srt_shape *shapes, size_t n_shapes, const srt_triangle *triangles,
+                     size_t n_triangles, const srt_material *materials, size_t n_materials,
+                     const srt_scene_data *scene_data) {
+	SRT_BIND(t);
+	if ((n_shapes && !shapes) || (n_triangles && !triangles) || (n_materials && !materials) || !scene_data)
+		return fail(t, SRT_ERR_INVALID, "null array with non-zero count");
+	if (n_shapes > 0x7fffffffu || n_triangles > 0x7fffffffu) return fail(t, SRT_ERR_INVALID, "scene too large");
+
+	// host-side repack of the (small) shape list into the SoA device records; validation of what the
+	// reference leaves unchecked (render.cl:412 material index, :325 triangle range)
+	std::vector<int4> hdr(n_shapes);
+	std::vector<float4> a(n_shapes), b(n_shapes), xf(4 * n_shapes);
+	std::vector<srt::ModelSpan> spans;
+	size_t soa = 0;
+	for (size_t i = 0; i < n_shapes; ++i) {
+		const srt_shape &s = shapes[i];
+		if (s.material < 0 || (size_t)s.material >= n_materials)
+			return fail(t, SRT_ERR_INVALID, "shape %zu: material %d out of range (%zu materials)", i, s.material, n_materials);
+		hdr[i] = make_int4(s.type, s.material, 0, 0);
+		a[i] = b[i] = make_float4(0, 0, 0, 0);
+		for (int c = 0; c < 4; ++c) xf[4 * i + c] = make_float4(0, 0, 0, 0);
+		if (s.type == SRT_SHAPE_SPHERE) {
+			a[i] = make_float4(s.shape.sphere.position.x, s.shape.sphere.position.y, s.shape.sphere.position.z, s.shape.sphere.radius);
+		} else if (s.type == SRT_SHAPE_PLANE) {
+			a[i] = make_float4(s.shape.plane.position.x, s.shape.plane.position.y, s.shape.plane.position.z, 0);
+			b[i] = make_float4(s.shape.plane.normal.x, s.shape.plane.normal.y, s.shape.plane.normal.z, 0);
+		} else if (s.type == SRT_SHAPE_MODEL) {
+			const srt_model &m = s.shape.model;
+			if ((size_t)m.triangle_index + m.num_triangles > n_triangles)
+				return fail(t, SRT_ERR_INVALID, "shape %zu: triangles [%u,+%u) exceed the %zu uploaded", i, m.triangle_index, m.num_triangles, n_triangles);
+			a[i] = make_float4(m.bounding_min.x, m.bounding_min.y, m.bounding_min.z, 0);
+			b[i] = make_float4(m.bounding_max.x, m.bounding_max.y, m.bounding_max.z, 0);
+			for (int c = 0; c < 4; ++c) xf[4 * i + c] = make_float4(m.transform[c].x, m.transform[c].y, m.transform[c].z, m.transform[c].w);
+			hdr[i].z = (int)soa;
+			hdr[i].w = (int)m.num_triangles;
+			if (m.num_triangles) spans.push_back(srt::ModelSpan{(int)i, (int)m.triangle_index, (int)soa, (int)m.num_triangles});
+			soa += m.num_triangles;
+			if (soa > 0x7fffffffu) return fail(t, SRT_ERR_INVALID, "too many model triangles");
+		} else {
+			return fail(t, SRT_ERR_INVALID, "shape %zu: unknown type %d", i, s.type);
+		}
+	}
+
+	SRT_CUDA(t, t->shape_hdr.reserve(n_shapes));
+	SRT_CUDA(t, t->shape_a.reserve(n_shapes));
+	SRT_CUDA(t, t->shape_b.reserve(n_shapes));
+	SRT_CUDA(t, t->model_xf.reserve(4 * n_shapes));
+	SRT_CUDA(t, t->materials.reserve(4 * n_materials));
+	SRT_CUDA(t, t->tri_aos.reserve(6 * n_triangles));
+	SRT_CUDA(t, t->tri_v0.reserve(soa));
+	SRT_CUDA(t, t->tri_e1.reserve(soa));
+	SRT_CUDA(t, t->tri_e2.reserve(soa));
+	SRT_CUDA(t, t->tri_n.reserve(3 * soa));
+	SRT_CUDA(t, t->spans.reserve(spans.size()));
+	cudaStream_t st = t->stream;
+	// the host vectors above die at return, and the caller may reuse its arrays: these copies are
+	// from pageable memory, which cudaMemcpyAsync stages before returning
+	if (n_shapes) {
+		SRT_CUDA(t, cudaMemcpyAsync(t->shape_hdr.ptr, hdr.data(), n_shapes * sizeof(int4), cudaMemcpyHostToDevice, st));
+		SRT_CUDA(t, cudaMemcpyAsync(t->shape_a.ptr, a.data(), n_shapes * sizeof(float4), cudaMemcpyHostToDevice, st));
+		SRT_CUDA(t, cudaMemcpyAsync(t->shape_b.ptr, b.data(), n_shapes * sizeof(float4), cudaMemcpyHostToDevice, st));
+		SRT_CUDA(t, cudaMemcpyAsync(t->model_xf.ptr, xf.data(), 4 * n_shapes * sizeof(float4), cudaMemcpyHostToDevice, st));
+	}
+	if (n_materials)
+		SRT_CUDA(t, cudaMemcpyAsync(t->materials.ptr, materials, n_materials * sizeof(srt_material), cudaMemcpyHostToDevice, st));
+	if (n_triangles)
+		SRT_CUDA(t, cudaMemcpyAsync(t->tri_aos.ptr, triangles, n_triangles * sizeof(srt_triangle), cudaMemcpyHostToDevice, st));
+	if (!spans.empty()) {
+		SRT_CUDA(t, cudaMemcpyAsync(t->spans.ptr, spans.data(), spans.size() * sizeof(srt::ModelSpan), cudaMemcpyHostToDevice, st));
+		const int total = (int)soa;
+		srt::prepare_triangles_kernel<<<(total + 255) / 256, 256, 0, st>>>(t->tri_aos.ptr, t->spans.ptr, (int)spans.size(), total,
+		                                                                  t->model_xf.ptr, t->tri_v0.ptr, t->tri_e1.ptr,
+		                                                                  t->tri_e2.ptr, t->tri_n.ptr);
+		SRT_CUDA(t, cudaGetLastError());
+	}
+	SRT_CUDA(t, cudaStreamSynchronize(st));  // copy-in semantics, like the blocking writes of tracer.cpp:76-86
+	t->n_shapes = n_shapes;
+	t->n_materials = n_materials;
+	t->n_soa_tris = soa;
+	t->has_models = soa > 0 || std::any_of(hdr.begin(), hdr.end(), [](const int4 &h) { return h.x == SRT_SHAPE_MODEL; });
+	t->scene_data = *scene_data;
+	t->scene_data.num_shapes = (int)n_shapes;  // tracer.cpp:94
+	t->have_scene = true;
+	return SRT_OK;
+}
+
+int srt_clear(srt_tracer *t) {
+	SRT_BIND(t);
+	SRT_CUDA(t, cudaMemsetAsync(t->canvas, 0, (size_t)t->width * t->height * sizeof(float4), t->stream));
+	return SRT_OK;
+}
+
+int srt_render(srt_tracer *t, const srt_render_data *rd) {
+	SRT_BIND(t);
+	return launch_render<false>(t, rd);
+}
+
+int srt_render_counted(srt_tracer *t, const srt_render_data *rd, srt_counters *counters) {
+	SRT_BIND(t);
+	if (!counters) return fail(t, SRT_ERR_INVALID, "counters is null");
+	SRT_CUDA(t, cudaMemsetAsync(t->counters, 0, sizeof(srt::Counters), t->stream));
+	if (int rc = launch_render<true>(t, rd)) return rc;
+	srt::Counters c{};
+	SRT_CUDA(t, cudaMemcpyAsync(&c, t->counters, sizeof c, cudaMemcpyDeviceToHost, t->stream));
+	SRT_CUDA(t, cudaStreamSynchronize(t->stream));
+	counters->samples += c.samples;
+	counters->bounces += c.bounces;
+	counters->tri_tests += c.tri_tests;
+	counters->aabb_pass += c.aabb_pass;
+	counters->hits += c.hits;
+	counters->sky += c.sky;
+	return SRT_OK;
+}
+
+int srt_resolve_device(srt_tracer *t, uint32_t num_steps) {
+	SRT_BIND(t);
+	const int n = t->width * t->height;
+	srt::average_kernel<<<(n + 255) / 256, 256, 0, t->stream>>>(num_steps, t->canvas, t->output, n);
+	SRT_CUDA(t, cudaGetLastError());
+	return SRT_OK;
+}
+
+int srt_resolve(srt_tracer *t, uint32_t num_steps, uint8_t *argb_out) {
+	SRT_BIND(t);
+	if (!argb_out) return fail(t, SRT_ERR_INVALID, "output is null");
+	if (int rc = srt_resolve_device(t, num_steps)) return rc;
+	const size_t bytes = (size_t)t->width * t->height * 4;
+	// D2H into the handle's pinned staging buffer, then into the caller's (pageable) vector:
+	// the blocking read of tracer.cpp:115
+	SRT_CUDA(t, cudaMemcpyAsync(t->pinned_out, t->output, bytes, cudaMemcpyDeviceToHost, t->stream));
+	SRT_CUDA(t, cudaStreamSynchronize(t->stream));
+	memcpy(argb_out, t->pinned_out, bytes);
+	return SRT_OK;
+}
+
+int srt_render_frame(srt_tracer *t, const srt_render_data *rd, uint32_t ticks_stopped, uint8_t *argb_out) {
+	if (int rc = srt_render(t, rd)) return rc;
+	return srt_resolve(t, ticks_stopped, argb_out);
+}
+
+int srt_set_row_bands(srt_tracer *t, int band_height, int band_index, int band_count) {
+	if (!t) return SRT_ERR_INVALID;
+	if (band_count <= 1) {
+		t->band_h = 1, t->band_i = 0, t->band_n = 1;
+		return SRT_OK;
+	}
+	if (band_height < 1 || band_index < 0 || band_index >= band_count) return fail(t, SRT_ERR_INVALID, "bad row bands");
+	t->band_h = band_height, t->band_i = band_index, t->band_n = band_count;
+	return SRT_OK;
+}
+
+int srt_read_canvas(srt_tracer *t, float *rgba_out) {
+	SRT_BIND(t);
+	if (!rgba_out) return fail(t, SRT_ERR_INVALID, "output is null");
+	SRT_CUDA(t, cudaMemcpyAsync(rgba_out, t->canvas, (size_t)t->width * t->height * sizeof(float4), cudaMemcpyDeviceToHost, t->stream));
+	SRT_CUDA(t, cudaStreamSynchronize(t->stream));
+	return SRT_OK;
+}
+
+int srt_write_canvas(srt_tracer *t, const float *rgba_in) {
+	SRT_BIND(t);
+	if (!rgba_in) return fail(t, SRT_ERR_INVALID, "input is null");
+	SRT_CUDA(t, cudaMemcpyAsync(t->canvas, rgba_in, (size_t)t->width * t->height * sizeof(float4), cudaMemcpyHostToDevice, t->stream));
+	SRT_CUDA(t, cudaStreamSynchronize(t->stream));
+	return SRT_OK;
+}
+
+int srt_canvas_device_ptr(srt_tracer *t, void **ptr, size_t *bytes) {
+	if (!t || !ptr) return SRT_ERR_INVALID;
+	*ptr = t->canvas;
+	if (bytes) *bytes = (size_t)t->width * t->height * sizeof(float4);
+	return SRT_OK;
+}
+
+int srt_output_device_ptr(srt_tracer *t, void **ptr, size_t *bytes) {
+	if (!t || !ptr) return SRT_ERR_INVALID;
+	*ptr = t->output;
+	if (bytes) *bytes = (size_t)t->width * t->height * 4;
+	return SRT_OK;
+}
+
+int srt_stream(srt_tracer *t, void **cuda_stream) {
+	if (!t || !cuda_stream) return SRT_ERR_INVALID;
+	*cuda_stream = t->stream;
+	return SRT_OK;
+}
+
+int srt_synchronize(srt_tracer *t) {
+	SRT_BIND(t);
+	SRT_CUDA(t, cudaStreamSynchronize(t->stream));
+	return SRT_OK;
+}
+
+int srt_debug_primary(srt_tracer *t, const srt_render_data *rd, int32_t *shape_idx, float *t_out) {
+	SRT_BIND(t);
+	if (!shape_idx || !t_out) return fail(t, SRT_ERR_INVALID, "output is null");
+	srt::RenderParams p{};
+	if (int rc = make_params(t, rd, p)) return rc;
+	const int n = p.width * p.height;
+	int *d_idx = nullptr;
+	float *d_t = nullptr;
+	SRT_CUDA(t, cudaMalloc(&d_idx, n * sizeof(int)));
+	if (cudaMalloc(&d_t, n * sizeof(float)) != cudaSuccess) {
+		cudaFree(d_idx);
+		return fail(t, SRT_ERR_CUDA, "cudaMalloc failed");
+	}
+	srt::primary_kernel<<<(n + 255) / 256, 256, 0, t->stream>>>(p, dev_scene(t), d_idx, d_t);
+	cudaError_t e = cudaGetLastError();
+	if (e == cudaSuccess) e = cudaMemcpyAsync(shape_idx, d_idx, n * sizeof(int), cudaMemcpyDeviceToHost, t->stream);
+	if (e == cudaSuccess) e = cudaMemcpyAsync(t_out, d_t, n * sizeof(float), cudaMemcpyDeviceToHost, t->stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(t->stream);
+	cudaFree(d_idx);
+	cudaFree(d_t);
+	if (e != cudaSuccess) return fail(t, SRT_ERR_CUDA, "debug_primary failed: %s", cudaGetErrorString(e));
+	return SRT_OK;
+}
+
+int srt_debug_math(srt_tracer *t, int op, const float *x, const float *y, float *out, size_t n) {
+	SRT_BIND(t);
+	if (!x || !y || !out) return fail(t, SRT_ERR_INVALID, "null array");
+	if (n == 0) return SRT_OK;
+	float *d = nullptr;
+	SRT_CUDA(t, cudaMalloc(&d, 3 * n * sizeof(float)));
+	cudaError_t e = cudaMemcpyAsync(d, x, n * sizeof(float), cudaMemcpyHostToDevice, t->stream);
+	if (e == cudaSuccess) e = cudaMemcpyAsync(d + n, y, n * sizeof(float), cudaMemcpyHostToDevice, t->stream);
+	if (e == cudaSuccess) {
+		srt::math_kernel<<<(unsigned)((n + 255) / 256), 256, 0, t->stream>>>(op, d, d + n, d + 2 * n, n);
+		e = cudaGetLastError();
+	}
+	if (e == cudaSuccess) e = cudaMemcpyAsync(out, d + 2 * n, n * sizeof(float), cudaMemcpyDeviceToHost, t->stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(t->stream);
+	cudaFree(d);
+	if (e != cudaSuccess) return fail(t, SRT_ERR_CUDA, "debug_math failed: %s", cudaGetErrorString(e));
+	return SRT_OK;
+}
+
+int srt_measure_fp32_peak(srt_tracer *t, double *tflops, double *sm_clock_mhz_est) {
+	SRT_BIND(t);
+	if (!tflops) return fail(t, SRT_ERR_INVALID, "tflops is null");
+	float *d = nullptr;
+	SRT_CUDA(t, cudaMalloc(&d, sizeof(float)));
+	cudaEvent_t e0, e1;
+	SRT_CUDA(t, cudaEventCreate(&e0));
+	SRT_CUDA(t, cudaEventCreate(&e1));
+	const int blocks = t->sm_count * 8, threads = 256, iters = 1 << 14;
+	double best = 0.0;
+	for (int rep = 0; rep < 6; ++rep) {
+		cudaEventRecord(e0, t->stream);
+		srt::fma_peak_kernel<<<blocks, threads, 0, t->stream>>>(d, iters, 1.0000001f, 1e-9f);
+		cudaEventRecord(e1, t->stream);
+		cudaError_t e = cudaStreamSynchronize(t->stream);
+		if (e != cudaSuccess) return fail(t, SRT_ERR_CUDA, "peak kernel failed: %s", cudaGetErrorString(e));
+		float ms = 0.f;
+		cudaEventElapsedTime(&ms, e0, e1);
+		double fl = 2.0 * 16.0 * (double)iters * (double)blocks * threads;
+		if (rep > 0) best = std::max(best, fl / (ms * 1e-3) / 1e12);
+	}
+	cudaEventDestroy(e0);
+	cudaEventDestroy(e1);
+	cudaFree(d);
+	*tflops = best;
+	if (sm_clock_mhz_est) *sm_clock_mhz_est = best * 1e12 / (2.0 * 128.0 * t->sm_count) / 1e6;
+	return SRT_OK;
+}
+
+int srt_render_time_ms(srt_tracer *t, double *total_ms, uint64_t *launches) {
+	SRT_BIND(t);
+	SRT_CUDA(t, cudaStreamSynchronize(t->stream));
+	double sum = 0.0;
+	for (auto &e : t->timing) {
+		float ms = 0.f;
+		SRT_CUDA(t, cudaEventElapsedTime(&ms, e.first, e.second));
+		sum += ms;
+		t->event_pool.push_back(e);
+	}
+	if (total_ms) *total_ms = sum;
+	if (launches) *launches = t->timing.size();
+	t->timing.clear();
+	return SRT_OK;
+}
+
+}  // extern "C"
