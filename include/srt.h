@@ -136,6 +136,7 @@ int srt_write_canvas(srt_tracer *t, const float *rgba_in);         /* restore an
 int srt_canvas_device_ptr(srt_tracer *t, void **ptr, size_t *bytes); /* for NCCL reduce of per-GPU canvases */
 int srt_output_device_ptr(srt_tracer *t, void **ptr, size_t *bytes); /* ARGB8 buffer, for gathers */
 int srt_resolve_device(srt_tracer *t, uint32_t num_steps);         /* `average` without the read-back */
+int srt_read_output(srt_tracer *t, uint8_t *argb_out);             /* read-back of the ARGB8 buffer alone; synchronises */
 int srt_stream(srt_tracer *t, void **cuda_stream);
 int srt_synchronize(srt_tracer *t);
 /* Shape index (-1 = miss) and distance of every pixel's sample-0 camera ray (parity gate). */

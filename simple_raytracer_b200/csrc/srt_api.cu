@@ -196,6 +196,10 @@ int launch_render(srt_tracer *t, const srt_render_data *rd) {
 	srt::render_kernel<COUNT><<<grid, srt::RENDER_THREADS, 0, t->stream>>>(p, sc, t->canvas, t->cursor, t->counters);
 	SRT_CUDA(t, cudaEventRecord(ev.second, t->stream));
 	SRT_CUDA(t, cudaGetLastError());
+	if (t->timing.size() >= 4096) {  // nobody is reading the timings: recycle
+		for (auto &e : t->timing) t->event_pool.push_back(e);
+		t->timing.clear();
+	}
 	t->timing.push_back(ev);
 	return SRT_OK;
 }
@@ -401,6 +405,16 @@ int srt_resolve_device(srt_tracer *t, uint32_t num_steps) {
 	const int n = t->width * t->height;
 	srt::average_kernel<<<(n + 255) / 256, 256, 0, t->stream>>>(num_steps, t->canvas, t->output, n);
 	SRT_CUDA(t, cudaGetLastError());
+	return SRT_OK;
+}
+
+int srt_read_output(srt_tracer *t, uint8_t *argb_out) {
+	SRT_BIND(t);
+	if (!argb_out) return fail(t, SRT_ERR_INVALID, "output is null");
+	const size_t bytes = (size_t)t->width * t->height * 4;
+	SRT_CUDA(t, cudaMemcpyAsync(t->pinned_out, t->output, bytes, cudaMemcpyDeviceToHost, t->stream));
+	SRT_CUDA(t, cudaStreamSynchronize(t->stream));
+	memcpy(argb_out, t->pinned_out, bytes);
 	return SRT_OK;
 }
 

@@ -50,6 +50,7 @@ def load_library():
         "srt_canvas_device_ptr": [vp, pp, ctypes.POINTER(sz)],
         "srt_output_device_ptr": [vp, pp, ctypes.POINTER(sz)],
         "srt_resolve_device": [vp, u32],
+        "srt_read_output": [vp, vp],
         "srt_stream": [vp, pp],
         "srt_synchronize": [vp],
         "srt_debug_primary": [vp, vp, vp, vp],
@@ -147,6 +148,11 @@ class Tracer:
 
     def resolve_device(self, num_steps):
         self._check(self._lib.srt_resolve_device(self._h, int(num_steps)))
+
+    def read_output(self):
+        out = np.empty((self.height, self.width, 4), np.uint8)
+        self._check(self._lib.srt_read_output(self._h, _p(out)))
+        return out
 
     def set_row_bands(self, band_height, band_index, band_count):
         self._check(self._lib.srt_set_row_bands(self._h, band_height, band_index, band_count))
