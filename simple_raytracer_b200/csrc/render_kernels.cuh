@@ -27,9 +27,7 @@ struct DevScene {
 	const int4 *shape_hdr;    // {type, material, soa_tri_begin, tri_count} in reference array order
 	const float4 *shape_a;    // sphere {c.xyz, r} | plane {p0.xyz, -} | model {bmin.xyz, -}
 	const float4 *shape_b;    // sphere {-}        | plane {n.xyz, -}  | model {bmax.xyz, -}
-	const float4 *tri_v0;     // world-space v0           (hot, 16 B each)
-	const float4 *tri_e1;     // world-space v1 - v0      (hot)
-	const float4 *tri_e2;     // world-space v2 - v0      (hot)
+	const float4 *tri_hot;    // 3 per triangle, 48 B stride: world-space v0, e1 = v1-v0, e2 = v2-v0 (+1 pad triangle)
 	const float4 *tri_n;      // 3 per triangle: object-space vertex normals (cold: winner only)
 	const float4 *model_xf;   // 4 per shape slot: model matrix columns      (cold)
 	const float4 *materials;  // 4 per material: the reference's 64-byte record as 4 x float4
@@ -48,8 +46,9 @@ struct RenderParams {
 	uint32_t time;
 	// row-band tiling (srt_set_row_bands)
 	int band_h, band_i, band_n;
-	int my_rows;            // number of rows this launch renders
+	int my_rows;               // number of rows this launch renders
 	unsigned int total_items;  // my_rows * width
+	float inv_ns;              // 1/num_samples when that is exact (num_samples a power of two), else 0
 };
 
 struct Counters {
@@ -62,21 +61,67 @@ struct Hit {
 	int tri;    // SoA triangle index of the winning triangle (models)
 };
 
-// ---- closest hit -----------------------------------------------------------------------------
-// reference closest_intersection, render.cl:293-378.  Shapes are visited in array order and a hit
-// replaces the current one only if strictly closer (:306,:332,:356), so the lowest index wins ties.
+#ifndef SRT_PHASE_PATIENCE
+#define SRT_PHASE_PATIENCE 1
+#endif
+constexpr int PHASE_PATIENCE = SRT_PHASE_PATIENCE;
+// Models with at most this many triangles are intersected inline during the shape scan; larger
+// ones park the lane until the warp runs a dense triangle phase (see render_kernel).
+constexpr int INLINE_MODEL_TRIS = 32;
+
+// One ray x triangle test: Moller-Trumbore (render.cl:243-275) on pre-transformed (v0, e1, e2), split in two.
+// tri_filter is a division-free conservative reject: with x = su * sign(det),
+//   x >  |det| * (1 + 1e-6)  =>  the exact u = (1/det) * su is certainly > 1
+//   x < -1e-6                =>  the exact u is certainly < 0 (and cannot underflow to -0)
+// so a triangle is dropped only when the exact test is certain to fail its u range check (proof in
+// DESIGN.md "Triangle filter").  Everything that survives runs tri_exact, the reference arithmetic.
+__device__ __forceinline__ bool tri_filter(const float4 v0, const float4 e1, const float4 e2, vec3 o, vec3 d) {
+	vec3 h = cross(d, xyz(e2));
+	float det = dot(xyz(e1), h);
+	vec3 s = o - xyz(v0);
+	float su = dot(s, h);
+	float x = __int_as_float(__float_as_int(su) ^ (__float_as_int(det) & 0x80000000));
+	float lim = fabsf(det) * 1.000001f;
+	return !(x > lim || x < -1e-6f);
+}
+__device__ __forceinline__ void tri_exact(const float4 v0, const float4 e1, const float4 e2, vec3 o, vec3 d, int shape,
+                                          int tri, Hit &hit) {
+	vec3 h = cross(d, xyz(e2));
+	float det = dot(xyz(e1), h);
+	// det == 0 (render.cl:253) needs no test of its own: then f = +-inf and t below is +-inf or NaN,
+	// which can never satisfy t < hit.t
+	float f = div_(1.0f, det);
+	vec3 s = o - xyz(v0);
+	float u = f * dot(s, h);
+	if (u < 0.0f || u > 1.0f) return;
+	vec3 q = cross(s, xyz(e1));
+	float v = f * dot(d, q);
+	if (v < 0.0f || u + v > 1.0f) return;
+	float t = f * dot(xyz(e2), q);
+	if (t > 0.0f && t < hit.t) {
+		hit.t = t;
+		hit.shape = shape;
+		hit.tri = tri;
+	}
+}
+__device__ __forceinline__ void test_triangle(const float4 v0, const float4 e1, const float4 e2, vec3 o, vec3 d,
+                                              int shape, int tri, Hit &hit) {
+	if (tri_filter(v0, e1, e2, o, d)) tri_exact(v0, e1, e2, o, d, shape, tri, hit);
+}
+
+// ---- shape scan ------------------------------------------------------------------------------
+// reference closest_intersection, render.cl:293-378, as a resumable scan.  Shapes are visited in
+// array order starting at `cursor`, and a hit replaces the current one only if strictly closer
+// (:306,:332,:356), so the lowest index wins ties.  A model whose AABB test passes (:319, with
+// tmax = the closest t so far) and that is too large to intersect inline stops the scan: the function
+// returns that shape index (the lane "parks" there) and the caller runs the triangles later, then
+// resumes at index + 1.  Returns -1 when the scan reached the end of the list.
 // Normal / position of the winner are reconstructed afterwards (finish_hit) instead of at every
 // improvement; only the last improvement is observable.
-template <bool COUNT>
-__device__ __forceinline__ Hit closest_hit(const DevScene &sc, vec3 o, vec3 d, Counters &cnt) {
-	Hit hit;
-	hit.t = __int_as_float(0x7f800000);
-	hit.shape = -1;
-	hit.tri = -1;
-	vec3 inv = mk(0.f, 0.f, 0.f);
-	if (sc.has_models) inv = mk(div_(1.0f, d.x), div_(1.0f, d.y), div_(1.0f, d.z));  // :297
-
-	for (int i = 0; i < sc.num_shapes; ++i) {
+template <bool COUNT, bool PARK, bool MODELS = true>
+__device__ __forceinline__ int scan_shapes(const DevScene &sc, vec3 o, vec3 d, vec3 inv, int cursor, Hit &hit,
+                                           Counters &cnt) {
+	for (int i = cursor; i < sc.num_shapes; ++i) {
 		const int4 hdr = __ldg(&sc.shape_hdr[i]);
 		const float4 a = __ldg(&sc.shape_a[i]);
 		if (hdr.x == SHAPE_SPHERE) {
@@ -106,7 +151,7 @@ __device__ __forceinline__ Hit closest_hit(const DevScene &sc, vec3 o, vec3 d, C
 					hit.shape = i;
 				}
 			}
-		} else if (hdr.x == SHAPE_MODEL) {
+		} else if (MODELS && hdr.x == SHAPE_MODEL) {
 			// intersection_aabb, :279-290, with tmax = current closest t (:319)
 			const float4 bb = __ldg(&sc.shape_b[i]);
 			float tmin = 0.0f, tmax = hit.t;
@@ -121,49 +166,20 @@ __device__ __forceinline__ Hit closest_hit(const DevScene &sc, vec3 o, vec3 d, C
 				tmin = max_(tmin, min_(t1, t2));
 				tmax = min_(tmax, max_(t1, t2));
 			}
-			const bool pass = tmin < tmax;
-			if (COUNT && pass) {
-				cnt.aabb_pass += 1;
-				cnt.tri_tests += (unsigned)hdr.w;
-			}
-			if (pass) {
-				// brute-force triangle loop, :324-350, on pre-transformed (v0, e1, e2).
-				// Moller-Trumbore (:243-275) with a division-free conservative reject placed
-				// before the exact test: a triangle is dropped early only when the exact test
-				// is certain to fail its `u` range check (proof in DESIGN.md "Triangle filter").
-				const int begin = hdr.z, count = hdr.w;
-#pragma unroll 2
-				for (int k = 0; k < count; ++k) {
-					const float4 v0 = __ldg(&sc.tri_v0[begin + k]);
-					const float4 e1 = __ldg(&sc.tri_e1[begin + k]);
-					const float4 e2 = __ldg(&sc.tri_e2[begin + k]);
-					vec3 h = cross(d, xyz(e2));
-					float det = dot(xyz(e1), h);
-					vec3 s = o - xyz(v0);
-					float su = dot(s, h);
-					// certain u > 1:  |su| > |det|*(1+1e-6) with equal signs
-					// certain u < 0:  opposite signs and |su| large enough not to underflow
-					float ad = fabsf(det), as = fabsf(su);
-					bool opposite = (__float_as_int(det) ^ __float_as_int(su)) < 0;
-					bool reject = opposite ? (as > 1e-6f) : (as > ad * 1.000001f);
-					if (reject || det == 0.0f) continue;
-					float f = div_(1.0f, det);
-					float u = f * su;
-					if (u < 0.0f || u > 1.0f) continue;
-					vec3 q = cross(s, xyz(e1));
-					float v = f * dot(d, q);
-					if (v < 0.0f || u + v > 1.0f) continue;
-					float t = f * dot(xyz(e2), q);
-					if (t > 0.0f && t < hit.t) {
-						hit.t = t;
-						hit.shape = i;
-						hit.tri = begin + k;
-					}
+			if (tmin < tmax) {
+				if (COUNT) {
+					cnt.aabb_pass += 1;
+					cnt.tri_tests += (unsigned)hdr.w;
 				}
+				if (PARK && hdr.w > INLINE_MODEL_TRIS) return i;
+				// brute-force triangle loop, :324-350
+				const float4 *tp = sc.tri_hot + 3 * (size_t)hdr.z;
+				for (int k = 0; k < hdr.w; ++k, tp += 3)
+					test_triangle(__ldg(tp), __ldg(tp + 1), __ldg(tp + 2), o, d, i, hdr.z + k, hit);
 			}
 		}
 	}
-	return hit;
+	return -1;
 }
 
 // Position and shading normal of the winning hit (render.cl:311-312, :337-343, :361-362) followed by
@@ -181,9 +197,9 @@ __device__ __forceinline__ void finish_hit(const DevScene &sc, const Hit &hit, v
 		n = xyz(__ldg(&sc.shape_b[hit.shape]));
 	} else {
 		// barycentric_weights, :223-241 (weights come back rotated: (w2, w0, w1))
-		vec3 v0 = xyz(__ldg(&sc.tri_v0[hit.tri]));
-		vec3 e1 = xyz(__ldg(&sc.tri_e1[hit.tri]));
-		vec3 e2 = xyz(__ldg(&sc.tri_e2[hit.tri]));
+		vec3 v0 = xyz(__ldg(&sc.tri_hot[3 * (size_t)hit.tri + 0]));
+		vec3 e1 = xyz(__ldg(&sc.tri_hot[3 * (size_t)hit.tri + 1]));
+		vec3 e2 = xyz(__ldg(&sc.tri_hot[3 * (size_t)hit.tri + 2]));
 		vec3 v2 = pos - v0;
 		float d00 = dot(e1, e1), d01 = dot(e1, e2), d11 = dot(e2, e2);
 		float d20 = dot(v2, e1), d21 = dot(v2, e2);
@@ -305,15 +321,158 @@ __device__ __forceinline__ void scatter(const DevScene &sc, int material, vec3 p
 }
 
 // ---- kernel `render` ---------------------------------------------------------------------------
-constexpr int RENDER_THREADS = 256;
+#ifndef SRT_RENDER_THREADS
+#define SRT_RENDER_THREADS 128
+#endif
+#ifndef SRT_MIN_BLOCKS
+#define SRT_MIN_BLOCKS 4
+#endif
+constexpr int RENDER_THREADS = SRT_RENDER_THREADS;
 
-template <bool COUNT>
-__global__ void __launch_bounds__(RENDER_THREADS, 2)
+// Dense triangle phase: a register-tiled outer product of (parked rays) x (one model's triangles).
+//
+//   * the model's hot stream (48 B per triangle: v0, e1, e2) arrives in a per-warp ring of
+//     shared-memory tiles filled by 1-D bulk async copies (cp.async.bulk -> SASS UBLKCP) completing on
+//     an mbarrier, TILE_STAGES tiles ahead of the consumer: no lane issues a global load;
+//   * every lane lifts TRIS_PER_LANE triangles of the current tile into REGISTERS (conflict-free
+//     LDS.128), so all 32 lanes are busy however few rays are parked;
+//   * the parked rays (origin, direction: 2 x float4 published once per phase) are broadcast one
+//     after the other; for each ray every lane runs the division-free filter on its own triangles
+//     and one VOTE per triangle slot hands the survivor mask of 32 triangles to the ray's owner lane;
+//   * after the sweep of a tile each owner runs the exact Moller-Trumbore on its few survivors, in
+//     triangle order, so ties resolve exactly as in the reference loop (render.cl:324-350).
+// Shared-memory traffic is 32 B per ray per tile instead of 48 B per ray per triangle, which is what
+// moves the loop from the shared-memory crossbar limit to the issue limit.
+#ifndef SRT_TRIS_PER_LANE
+#define SRT_TRIS_PER_LANE 4
+#endif
+#ifndef SRT_TILE_STAGES
+#define SRT_TILE_STAGES 2
+#endif
+constexpr int TRIS_PER_LANE = SRT_TRIS_PER_LANE;
+constexpr int TILE_TRIS = 32 * TRIS_PER_LANE;
+constexpr int TILE_STAGES = SRT_TILE_STAGES;
+constexpr int TILE_BYTES = TILE_TRIS * 48;
+constexpr int RING_BYTES = TILE_STAGES * TILE_BYTES;
+constexpr int RAYS_BYTES = 32 * 32;  // 32 rays x (origin float4, direction float4)
+constexpr int RENDER_WARPS = RENDER_THREADS / 32;
+constexpr int WARP_SMEM_BYTES = RING_BYTES + RAYS_BYTES;
+constexpr int RENDER_SMEM_BYTES = RENDER_WARPS * (WARP_SMEM_BYTES + TILE_STAGES * 8);
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void bulk_load_tile(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+	             "l"(src), "r"(bytes), "r"(bar)
+	             : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+	asm volatile(
+	    "{\n"
+	    ".reg .pred p;\n"
+	    "WAIT_%=:\n"
+	    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+	    "@!p bra WAIT_%=;\n"
+	    "}\n" ::"r"(bar),
+	    "r"(parity)
+	    : "memory");
+}
+
+// n, tri_begin, shape: the model being swept (warp-uniform); active: this lane's ray is parked at it.
+__device__ __forceinline__ void triangle_phase(const DevScene &sc, int n, int tri_begin, int shape, bool active, vec3 o,
+                                               vec3 d, Hit &hit, float4 *wsmem, uint32_t wsmem_s, uint32_t bars_s,
+                                               uint32_t &parity, int lane) {
+	const unsigned FULL = 0xffffffffu;
+	const float4 *tiles = wsmem;
+	float4 *rays = wsmem + RING_BYTES / 16;
+	const char *src = reinterpret_cast<const char *>(sc.tri_hot + 3 * (size_t)tri_begin);
+	const int ntiles = (n + TILE_TRIS - 1) / TILE_TRIS;
+	auto issue = [&](int t) {
+		const int st = t % TILE_STAGES;
+		bulk_load_tile(wsmem_s + st * TILE_BYTES, src + (size_t)t * TILE_BYTES, (uint32_t)min(TILE_TRIS, n - t * TILE_TRIS) * 48u,
+		               bars_s + st * 8);
+	};
+	if (lane == 0)
+		for (int t = 0; t < min(ntiles, TILE_STAGES); ++t) issue(t);
+	if (active) {
+		rays[2 * lane] = make_float4(o.x, o.y, o.z, 0.f);
+		rays[2 * lane + 1] = make_float4(d.x, d.y, d.z, 0.f);
+	}
+	const unsigned ray_mask = __ballot_sync(FULL, active);
+	__syncwarp();
+
+	for (int t = 0; t < ntiles; ++t) {
+		const int st = t % TILE_STAGES;
+		mbar_wait(bars_s + st * 8, (parity >> st) & 1u);
+		parity ^= 1u << st;
+		const float4 *tile = tiles + st * (TILE_TRIS * 3);
+		const int cnt = min(TILE_TRIS, n - t * TILE_TRIS);
+		// my triangles of this tile: slot q holds triangle q*32 + lane (bit `lane` of the slot's vote)
+		float4 tv0[TRIS_PER_LANE], te1[TRIS_PER_LANE], te2[TRIS_PER_LANE];
+		uint32_t valid[TRIS_PER_LANE];  // beyond the list the tile holds stale shared memory: votes are masked
+#pragma unroll
+		for (int q = 0; q < TRIS_PER_LANE; ++q) {
+			const int j = q * 32 + lane;
+			tv0[q] = tile[3 * j], te1[q] = tile[3 * j + 1], te2[q] = tile[3 * j + 2];
+			const int left = cnt - q * 32;
+			valid[q] = left >= 32 ? 0xffffffffu : (left <= 0 ? 0u : (1u << left) - 1u);
+		}
+		uint32_t cand[TRIS_PER_LANE];
+#pragma unroll
+		for (int q = 0; q < TRIS_PER_LANE; ++q) cand[q] = 0;
+		for (unsigned rm = ray_mask; rm; rm &= rm - 1) {  // warp-uniform loop over the parked rays
+			const int r = __ffs(rm) - 1;
+			const float4 ro4 = rays[2 * r], rd4 = rays[2 * r + 1];  // broadcast
+			const vec3 ro = xyz(ro4), rd = xyz(rd4);
+#pragma unroll
+			for (int q = 0; q < TRIS_PER_LANE; ++q) {
+				const unsigned v = __ballot_sync(FULL, tri_filter(tv0[q], te1[q], te2[q], ro, rd));
+				if (lane == r) cand[q] = v;
+			}
+		}
+		if (active) {  // exact test of my ray's survivors, lowest triangle index first
+#pragma unroll
+			for (int q = 0; q < TRIS_PER_LANE; ++q) {
+				uint32_t c = cand[q] & valid[q];
+				while (c) {
+					const int j = q * 32 + __ffs(c) - 1;
+					c &= c - 1;
+					tri_exact(tile[3 * j], tile[3 * j + 1], tile[3 * j + 2], o, d, shape, tri_begin + t * TILE_TRIS + j, hit);
+				}
+			}
+		}
+		__syncwarp();  // every lane is done reading this stage before it is refilled
+		if (lane == 0 && t + TILE_STAGES < ntiles) issue(t + TILE_STAGES);
+	}
+}
+
+// MODELS = false is the build for scenes without any model shape: no triangle code, no shared memory,
+// fewer registers (more resident warps for the latency-bound analytic path).
+template <bool COUNT, bool MODELS>
+__global__ void __launch_bounds__(RENDER_THREADS, SRT_MIN_BLOCKS)
 render_kernel(const __grid_constant__ RenderParams p, const __grid_constant__ DevScene sc,
               float4 *__restrict__ canvas, unsigned int *__restrict__ cursor, Counters *__restrict__ counters) {
 	const unsigned FULL = 0xffffffffu;
 	const int lane = threadIdx.x & 31;
 	Counters cnt = {0, 0, 0, 0, 0, 0};
+
+	// per-warp ring of triangle tiles + one mbarrier per stage
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	const int warp = threadIdx.x >> 5;
+	float4 *wsmem = reinterpret_cast<float4 *>(smem_raw + warp * WARP_SMEM_BYTES);
+	const uint32_t wsmem_s = smem_u32(wsmem);
+	const uint32_t bars_s = smem_u32(smem_raw + RENDER_WARPS * WARP_SMEM_BYTES + warp * (TILE_STAGES * 8));
+	uint32_t parity = 0;
+	if (MODELS) {
+		if (lane == 0) {
+			for (int st = 0; st < TILE_STAGES; ++st) mbar_init(bars_s + st * 8, 1);
+			asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+		}
+		__syncwarp();
+	}
 
 	bool alive = true;
 	int pix = -1, gx = 0, gy = 0;
@@ -322,6 +481,12 @@ render_kernel(const __grid_constant__ RenderParams p, const __grid_constant__ De
 	bool fresh = false;          // a camera ray must be generated
 	uint32_t seed = 0;
 	vec3 o = mk(0, 0, 0), d = mk(0, 0, 1), mask = mk(1, 1, 1), color = mk(0, 0, 0), pixsum = mk(0, 0, 0);
+	// closest-hit scan state of the current bounce
+	vec3 inv = mk(0, 0, 0);
+	Hit hit = {0.f, -1, -1};
+	int scan_at = -1;  // next shape to visit; -1 = a new bounce has to be started
+	int park = -1;     // shape index of the model this lane waits to run triangles for
+	int waited = 0;    // warp-uniform: trips spent with parked lanes waiting for company
 	const float ns_f = (float)p.num_samples;
 
 	for (;;) {
@@ -335,9 +500,15 @@ render_kernel(const __grid_constant__ RenderParams p, const __grid_constant__ De
 			if (need_pixel) {
 				if (pix >= 0) {  // canvas[id] += color / num_samples, :520-522
 					float4 c = canvas[pix];
-					c.x += div_(pixsum.x, ns_f);
-					c.y += div_(pixsum.y, ns_f);
-					c.z += div_(pixsum.z, ns_f);
+					if (p.inv_ns != 0.0f) {  // x / 2^k == x * 2^-k exactly
+						c.x += pixsum.x * p.inv_ns;
+						c.y += pixsum.y * p.inv_ns;
+						c.z += pixsum.z * p.inv_ns;
+					} else {
+						c.x += div_(pixsum.x, ns_f);
+						c.y += div_(pixsum.y, ns_f);
+						c.z += div_(pixsum.z, ns_f);
+					}
 					canvas[pix] = c;
 				}
 				const unsigned int item = base + __popc(need & ((1u << lane) - 1u));
@@ -356,55 +527,91 @@ render_kernel(const __grid_constant__ RenderParams p, const __grid_constant__ De
 			}
 		}
 		if (!__any_sync(FULL, alive)) break;
-		if (alive) {
-		if (fresh) {  // start path `sample` of pixel `pix`, :496-516
-			seed = ((uint32_t)sample + (uint32_t)pix * (uint32_t)p.num_samples) * p.time * 5304u;
-			camera_ray(p, gx, gy, seed, o, d);
-			mask = mk(1, 1, 1);
-			color = mk(0, 0, 0);
-			bounce = 0;
-			fresh = false;
-			if (COUNT) cnt.samples += 1;
-		}
 
-		// -- one bounce, :403-468
-		if (COUNT) cnt.bounces += 1;
-		const Hit hit = closest_hit<COUNT>(sc, o, d, cnt);
-		bool done;
-		if (hit.shape >= 0) {
-			if (COUNT) cnt.hits += 1;
-			vec3 pos, n;
-			bool front;
-			int material;
-			finish_hit(sc, hit, o, d, pos, n, front, material);
-			if (p.show_normals) {  // :407-410
-				color = mk(fma_(n.x, 0.5f, 0.5f), fma_(n.y, 0.5f, 0.5f), fma_(n.z, 0.5f, 0.5f));
-				done = true;
-			} else {
-				const float4 m0 = __ldg(&sc.materials[4 * material + 0]);
-				const float4 em = __ldg(&sc.materials[4 * material + 3]);
-				color = color + (mask * xyz(em)) * m0.w;  // :413
-				if (bounce == p.num_bounces - 1) {         // :415-416
+		if (alive && park < 0) {
+			if (fresh) {  // start path `sample` of pixel `pix`, :496-516
+				seed = ((uint32_t)sample + (uint32_t)pix * (uint32_t)p.num_samples) * p.time * 5304u;
+				camera_ray(p, gx, gy, seed, o, d);
+				mask = mk(1, 1, 1);
+				color = mk(0, 0, 0);
+				bounce = 0;
+				fresh = false;
+				scan_at = -1;
+				if (COUNT) cnt.samples += 1;
+			}
+			if (scan_at < 0) {  // new bounce: closest_intersection prologue, :294-297
+				if (COUNT) cnt.bounces += 1;
+				hit.t = __int_as_float(0x7f800000);
+				hit.shape = -1;
+				hit.tri = -1;
+				if (MODELS) inv = mk(div_(1.0f, d.x), div_(1.0f, d.y), div_(1.0f, d.z));
+				scan_at = 0;
+			}
+			park = scan_shapes<COUNT, true, MODELS>(sc, o, d, inv, scan_at, hit, cnt);
+
+			if (park < 0) {  // scan complete: shade this bounce, :404-468
+				scan_at = -1;
+				bool done;
+				if (hit.shape >= 0) {
+					if (COUNT) cnt.hits += 1;
+					vec3 pos, n;
+					bool front;
+					int material;
+					finish_hit(sc, hit, o, d, pos, n, front, material);
+					if (p.show_normals) {  // :407-410
+						color = mk(fma_(n.x, 0.5f, 0.5f), fma_(n.y, 0.5f, 0.5f), fma_(n.z, 0.5f, 0.5f));
+						done = true;
+					} else {
+						const float4 m0 = __ldg(&sc.materials[4 * material + 0]);
+						const float4 em = __ldg(&sc.materials[4 * material + 3]);
+						color = color + (mask * xyz(em)) * m0.w;  // :413
+						if (bounce == p.num_bounces - 1) {         // :415-416
+							done = true;
+						} else {
+							const float4 m1 = __ldg(&sc.materials[4 * material + 1]);
+							scatter(sc, material, pos, n, front, seed, o, d, mask, m0, m1);
+							bounce += 1;
+							done = false;
+						}
+					}
+				} else {  // :463-467
+					if (COUNT) cnt.sky += 1;
+					mask = mask * sky_box(sc, d);
+					color = color + mask;
 					done = true;
-				} else {
-					const float4 m1 = __ldg(&sc.materials[4 * material + 1]);
-					scatter(sc, material, pos, n, front, seed, o, d, mask, m0, m1);
-					bounce += 1;
-					done = false;
+				}
+				if (done) {
+					pixsum = pixsum + color;  // :518
+					sample += 1;
+					fresh = true;
 				}
 			}
-		} else {  // :463-467
-			if (COUNT) cnt.sky += 1;
-			mask = mask * sky_box(sc, d);
-			color = color + mask;
-			done = true;
 		}
-		if (done) {
-			pixsum = pixsum + color;  // :518
-			sample += 1;
-			fresh = true;
+
+		// -- dense triangle phase.  Lane utilisation inside the phase does not depend on how many rays are
+		// parked (the lanes hold triangles there), so it runs after at most PHASE_PATIENCE trips of waiting
+		// for company; parked lanes get back to tracing as soon as possible.
+		const unsigned parked = MODELS ? __ballot_sync(FULL, park >= 0) : 0u;
+		if (MODELS && parked) {
+			const unsigned movable = __ballot_sync(FULL, alive && park < 0);
+			if (movable == 0 || waited >= PHASE_PATIENCE) {
+				// the model most lanes wait for (ties: the lower shape index)
+				const unsigned same = __match_any_sync(FULL, park);
+				const int votes = park >= 0 ? (__popc(same) << 20) | (0xfffff - min(park, 0xfffff)) : 0;
+				const int best = __reduce_max_sync(FULL, votes);
+				const int model = 0xfffff - (best & 0xfffff);
+				const int4 hdr = __ldg(&sc.shape_hdr[model]);
+				const bool active = park == model;
+				triangle_phase(sc, hdr.w, hdr.z, model, active, o, d, hit, wsmem, wsmem_s, bars_s, parity, lane);
+				if (active) {
+					scan_at = park + 1;
+					park = -1;
+				}
+				waited = 0;
+			} else {
+				waited += 1;
+			}
 		}
-		}  // alive
 	}
 
 	if (COUNT) {
@@ -451,7 +658,9 @@ primary_kernel(const __grid_constant__ RenderParams p, const __grid_constant__ D
 	vec3 o, d;
 	camera_ray(p, gx, gy, seed, o, d);
 	Counters cnt = {0, 0, 0, 0, 0, 0};
-	Hit hit = closest_hit<false>(sc, o, d, cnt);
+	Hit hit = {__int_as_float(0x7f800000), -1, -1};
+	vec3 inv = mk(div_(1.0f, d.x), div_(1.0f, d.y), div_(1.0f, d.z));
+	scan_shapes<false, false>(sc, o, d, inv, 0, hit, cnt);
 	shape_idx[id] = hit.shape;
 	t_out[id] = hit.t;
 }
@@ -468,8 +677,8 @@ struct ModelSpan {
 };
 __global__ void __launch_bounds__(256)
 prepare_triangles_kernel(const float4 *__restrict__ aos /* 6 float4 per triangle */, const ModelSpan *__restrict__ spans,
-                         int n_spans, int total, const float4 *__restrict__ model_xf, float4 *__restrict__ v0_out,
-                         float4 *__restrict__ e1_out, float4 *__restrict__ e2_out, float4 *__restrict__ n_out) {
+                         int n_spans, int total, const float4 *__restrict__ model_xf, float4 *__restrict__ hot_out,
+                         float4 *__restrict__ n_out) {
 	int g = blockIdx.x * blockDim.x + threadIdx.x;
 	if (g >= total) return;
 	int lo = 0, hi = n_spans - 1;  // last span with dst_begin <= g
@@ -491,9 +700,9 @@ prepare_triangles_kernel(const float4 *__restrict__ aos /* 6 float4 per triangle
 		n_out[3 * (size_t)g + j] = tri[2 * j];
 	}
 	vec3 e1 = w[1] - w[0], e2 = w[2] - w[0];
-	v0_out[g] = make_float4(w[0].x, w[0].y, w[0].z, 0.f);
-	e1_out[g] = make_float4(e1.x, e1.y, e1.z, 0.f);
-	e2_out[g] = make_float4(e2.x, e2.y, e2.z, 0.f);
+	hot_out[3 * (size_t)g + 0] = make_float4(w[0].x, w[0].y, w[0].z, 0.f);
+	hot_out[3 * (size_t)g + 1] = make_float4(e1.x, e1.y, e1.z, 0.f);
+	hot_out[3 * (size_t)g + 2] = make_float4(e2.x, e2.y, e2.z, 0.f);
 }
 
 // ---- device math self-test -------------------------------------------------------------------

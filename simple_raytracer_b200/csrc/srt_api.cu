@@ -73,7 +73,7 @@ struct srt_tracer {
 
 	DevBuf<int4> shape_hdr;
 	DevBuf<float4> shape_a, shape_b, model_xf, materials;
-	DevBuf<float4> tri_aos, tri_v0, tri_e1, tri_e2, tri_n;
+	DevBuf<float4> tri_aos, tri_hot, tri_n;
 	DevBuf<srt::ModelSpan> spans;
 	size_t n_shapes = 0, n_materials = 0, n_soa_tris = 0;
 	bool has_models = false;
@@ -81,7 +81,7 @@ struct srt_tracer {
 	bool have_scene = false;
 
 	int band_h = 1, band_i = 0, band_n = 1;
-	int render_grid = 0, render_grid_counted = 0;
+	int render_grid[2][2] = {{0, 0}, {0, 0}};  // [counted][models]
 
 	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing;  // render launches since last query
 	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> event_pool;
@@ -120,9 +120,7 @@ srt::DevScene dev_scene(const srt_tracer *t) {
 	s.shape_hdr = t->shape_hdr.ptr;
 	s.shape_a = t->shape_a.ptr;
 	s.shape_b = t->shape_b.ptr;
-	s.tri_v0 = t->tri_v0.ptr;
-	s.tri_e1 = t->tri_e1.ptr;
-	s.tri_e2 = t->tri_e2.ptr;
+	s.tri_hot = t->tri_hot.ptr;
 	s.tri_n = t->tri_n.ptr;
 	s.model_xf = t->model_xf.ptr;
 	s.materials = t->materials.ptr;
@@ -154,6 +152,7 @@ int make_params(srt_tracer *t, const srt_render_data *rd, srt::RenderParams &p) 
 	p.show_normals = rd->show_normals ? 1 : 0;
 	memcpy(p.c2w, rd->camera_to_world, sizeof p.c2w);
 	p.time = rd->time;
+	p.inv_ns = (rd->num_samples & (rd->num_samples - 1)) == 0 ? 1.0f / (float)rd->num_samples : 0.0f;
 	p.band_h = t->band_h;
 	p.band_i = t->band_i;
 	p.band_n = t->band_n;
@@ -168,14 +167,15 @@ int make_params(srt_tracer *t, const srt_render_data *rd, srt::RenderParams &p) 
 	return SRT_OK;
 }
 
-template <bool COUNT>
-int launch_render(srt_tracer *t, const srt_render_data *rd) {
-	srt::RenderParams p{};
-	if (int rc = make_params(t, rd, p)) return rc;
-	int &grid = COUNT ? t->render_grid_counted : t->render_grid;
+template <bool COUNT, bool MODELS>
+int launch_render_impl(srt_tracer *t, const srt::RenderParams &p) {
+	auto kernel = srt::render_kernel<COUNT, MODELS>;
+	const int smem = MODELS ? srt::RENDER_SMEM_BYTES : 0;
+	int &grid = t->render_grid[COUNT ? 1 : 0][MODELS ? 1 : 0];
 	if (grid == 0) {
 		int per_sm = 0;
-		SRT_CUDA(t, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, srt::render_kernel<COUNT>, srt::RENDER_THREADS, 0));
+		if (smem) SRT_CUDA(t, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+		SRT_CUDA(t, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, srt::RENDER_THREADS, smem));
 		grid = std::max(per_sm, 1) * t->sm_count;  // persistent: one full wave, work pulled from the cursor
 	}
 	SRT_CUDA(t, cudaMemsetAsync(t->cursor, 0, sizeof(unsigned int), t->stream));
@@ -188,12 +188,8 @@ int launch_render(srt_tracer *t, const srt_render_data *rd) {
 		SRT_CUDA(t, cudaEventCreate(&ev.second));
 	}
 	const srt::DevScene sc = dev_scene(t);
-	if (p.num_bounces == 0 || p.total_items == 0) {  // render.cl:403: zero bounces adds zero radiance
-		t->event_pool.push_back(ev);
-		return SRT_OK;
-	}
 	SRT_CUDA(t, cudaEventRecord(ev.first, t->stream));
-	srt::render_kernel<COUNT><<<grid, srt::RENDER_THREADS, 0, t->stream>>>(p, sc, t->canvas, t->cursor, t->counters);
+	kernel<<<grid, srt::RENDER_THREADS, smem, t->stream>>>(p, sc, t->canvas, t->cursor, t->counters);
 	SRT_CUDA(t, cudaEventRecord(ev.second, t->stream));
 	SRT_CUDA(t, cudaGetLastError());
 	if (t->timing.size() >= 4096) {  // nobody is reading the timings: recycle
@@ -202,6 +198,14 @@ int launch_render(srt_tracer *t, const srt_render_data *rd) {
 	}
 	t->timing.push_back(ev);
 	return SRT_OK;
+}
+
+template <bool COUNT>
+int launch_render(srt_tracer *t, const srt_render_data *rd) {
+	srt::RenderParams p{};
+	if (int rc = make_params(t, rd, p)) return rc;
+	if (p.num_bounces == 0 || p.total_items == 0) return SRT_OK;  // render.cl:403: zero bounces add zero radiance
+	return t->has_models ? launch_render_impl<COUNT, true>(t, p) : launch_render_impl<COUNT, false>(t, p);
 }
 
 }  // namespace
@@ -280,7 +284,7 @@ int srt_destroy(srt_tracer *t) {
 	cudaFree(t->counters);
 	cudaFree(t->sky);
 	t->shape_hdr.release(), t->shape_a.release(), t->shape_b.release(), t->model_xf.release(), t->materials.release();
-	t->tri_aos.release(), t->tri_v0.release(), t->tri_e1.release(), t->tri_e2.release(), t->tri_n.release(), t->spans.release();
+	t->tri_aos.release(), t->tri_hot.release(), t->tri_n.release(), t->spans.release();
 	if (t->stream) cudaStreamDestroy(t->stream);
 	delete t;
 	return SRT_OK;
@@ -335,9 +339,7 @@ int srt_upload_scene(srt_tracer *t, const srt_shape *shapes, size_t n_shapes, co
 	SRT_CUDA(t, t->model_xf.reserve(4 * n_shapes));
 	SRT_CUDA(t, t->materials.reserve(4 * n_materials));
 	SRT_CUDA(t, t->tri_aos.reserve(6 * n_triangles));
-	SRT_CUDA(t, t->tri_v0.reserve(soa));
-	SRT_CUDA(t, t->tri_e1.reserve(soa));
-	SRT_CUDA(t, t->tri_e2.reserve(soa));
+	SRT_CUDA(t, t->tri_hot.reserve(3 * soa));
 	SRT_CUDA(t, t->tri_n.reserve(3 * soa));
 	SRT_CUDA(t, t->spans.reserve(spans.size()));
 	cudaStream_t st = t->stream;
@@ -357,8 +359,7 @@ int srt_upload_scene(srt_tracer *t, const srt_shape *shapes, size_t n_shapes, co
 		SRT_CUDA(t, cudaMemcpyAsync(t->spans.ptr, spans.data(), spans.size() * sizeof(srt::ModelSpan), cudaMemcpyHostToDevice, st));
 		const int total = (int)soa;
 		srt::prepare_triangles_kernel<<<(total + 255) / 256, 256, 0, st>>>(t->tri_aos.ptr, t->spans.ptr, (int)spans.size(), total,
-		                                                                  t->model_xf.ptr, t->tri_v0.ptr, t->tri_e1.ptr,
-		                                                                  t->tri_e2.ptr, t->tri_n.ptr);
+		                                                                  t->model_xf.ptr, t->tri_hot.ptr, t->tri_n.ptr);
 		SRT_CUDA(t, cudaGetLastError());
 	}
 	SRT_CUDA(t, cudaStreamSynchronize(st));  // copy-in semantics, like the blocking writes of tracer.cpp:76-86

@@ -18,7 +18,7 @@ import numpy as np
 from .records import COUNTERS, MATERIAL, RENDER_DATA, SCENE_DATA, SHAPE, TRIANGLE, concat_records
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsrt_b200.so")
+LIB_PATH = os.environ.get("SRT_LIB") or os.path.join(_HERE, "libsrt_b200.so")  # SRT_LIB: developer builds
 _lib = None
 
 
