@@ -57,7 +57,7 @@ class ClockSampler:
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -254,7 +254,7 @@ def main():
     except OSError:
         pass
     canvas_bytes = pixels * 32  # canvas RMW per launch: the only HBM-resident traffic of the kernel
-    roofline = {"bound": "fp32", "kernel": "srt::render_kernel<false>", "achieved": achieved, "peak": peak_tf,
+    roofline = {"bound": "fp32", "kernel": "srt::render_kernel<COUNT=false, MODELS=%s>" % ("true" if len(scene.triangles) else "false"), "achieved": achieved, "peak": peak_tf,
                 "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,
                 "peak_source": "FMA-chain micro-benchmark measured in this run (srt_measure_fp32_peak); "
                                f"nominal 148 SM x 128 x 2 x 1.965 GHz = {nominal:.1f}",

@@ -327,6 +327,9 @@ __device__ __forceinline__ void scatter(const DevScene &sc, int material, vec3 p
 #ifndef SRT_MIN_BLOCKS
 #define SRT_MIN_BLOCKS 4
 #endif
+#ifndef SRT_MIN_BLOCKS_ANALYTIC
+#define SRT_MIN_BLOCKS_ANALYTIC 6
+#endif
 constexpr int RENDER_THREADS = SRT_RENDER_THREADS;
 
 // Dense triangle phase: a register-tiled outer product of (parked rays) x (one model's triangles).
@@ -452,7 +455,7 @@ __device__ __forceinline__ void triangle_phase(const DevScene &sc, int n, int tr
 // MODELS = false is the build for scenes without any model shape: no triangle code, no shared memory,
 // fewer registers (more resident warps for the latency-bound analytic path).
 template <bool COUNT, bool MODELS>
-__global__ void __launch_bounds__(RENDER_THREADS, SRT_MIN_BLOCKS)
+__global__ void __launch_bounds__(RENDER_THREADS, MODELS ? SRT_MIN_BLOCKS : SRT_MIN_BLOCKS_ANALYTIC)
 render_kernel(const __grid_constant__ RenderParams p, const __grid_constant__ DevScene sc,
               float4 *__restrict__ canvas, unsigned int *__restrict__ cursor, Counters *__restrict__ counters) {
 	const unsigned FULL = 0xffffffffu;

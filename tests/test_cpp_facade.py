@@ -1,0 +1,77 @@
+"""include/tracer.hpp: the C++ facade with the reference Tracer's surface, driven by examples/headless.cpp
+the way src/main.cpp drives the reference."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "build", "headless_test")
+
+
+def build_harness():
+    os.makedirs(os.path.dirname(EXE), exist_ok=True)
+    lib = os.path.join(ROOT, "simple_raytracer_b200")
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "headless.cpp"), "-L" + lib, "-lsrt_b200",
+                           "-Wl,-rpath," + lib, "-o", EXE])
+
+
+def test_facade_compiles_and_links():
+    build_harness()
+    assert os.path.exists(EXE)
+
+
+def test_c_header_is_plain_c(tmp_path):
+    """include/srt.h must be consumable from C (the cgo / ctypes / JNI side of the boundary)."""
+    src = tmp_path / "t.c"
+    src.write_text('#include "srt.h"\n_Static_assert(sizeof(srt_shape) == 128 && sizeof(srt_triangle) == 96 && '
+                   'sizeof(srt_material) == 64 && sizeof(srt_render_data) == 112 && sizeof(srt_scene_data) == 96, "abi");\n'
+                   "int main(void) { return srt_abi_version() == SRT_ABI_VERSION ? 0 : 1; }\n")
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"), "-c", str(src),
+                           "-o", str(tmp_path / "t.o")])
+
+
+@pytest.mark.gpu
+def test_headless_harness_matches_python_path_and_oracle(tmp_path, oracle_lib):
+    from simple_raytracer_b200 import scenes
+    from simple_raytracer_b200.tracer import Tracer
+    build_harness()
+    w, h, frames = 200, 120, 3
+    out = tmp_path / "o.ppm"
+    subprocess.check_call([EXE, str(out), str(w), str(h), str(frames)])
+    data = out.read_bytes()
+    header = f"P6 {w} {h} 255\n".encode()
+    assert data.startswith(header)
+    got = np.frombuffer(data[len(header):], np.uint8).reshape(h, w, 3)
+
+    # the same scene and protocol through the Python mirror
+    F = np.float32
+    sky = np.ones((32, 64, 4), F)
+    v = ((np.arange(32, dtype=F) + F(0.5)) / F(32))[:, None]
+    sky[..., 0], sky[..., 1], sky[..., 2] = F(0.25) + F(0.3) * v, F(0.35) + F(0.35) * v, F(0.5) + F(0.45) * v
+    mats = [scenes.material((0.8, 0.8, 0.8)),
+            scenes.material((1, 1, 1), smoothness=1.0, transmittance=1.0, refraction_index=1.5),
+            scenes.material((0.25, 0.4, 0.95), smoothness=0.95, metallic=1.0),
+            scenes.material((1, 0.2, 0.15), emission=(1, 0.15, 0.1), emission_strength=5.0)]
+    shapes = [scenes.plane(0, (0, -2, 0), (0, 1, 0)), scenes.sphere(0, (-3.2, 0, -3), 2.0),
+              scenes.sphere(1, (0.6, -0.8, -0.5), 1.2), scenes.sphere(2, (3.4, -0.6, -2.6), 1.4),
+              scenes.sphere(3, (-0.4, -1.3, -4.6), 0.7)]
+    sc = scenes.Scene("headless", w, h, 2, 10, frames, scenes._stack(shapes, scenes.SHAPE), np.zeros(0, scenes.TRIANGLE),
+                      scenes._stack(mats, scenes.MATERIAL), scenes.camera_matrix((0, 0.5, 5.5)))
+    sc.scene_data["sun_color"] = [1.0, 1.0, F(0xD3) / F(255.0)]
+    inv = F(1.0) / np.sqrt(F(2.0))
+    sc.scene_data["sun_direction"] = [inv, -inv, 0.0]
+    tr = Tracer(w, h, sky)
+    tr.scene_data[:] = sc.scene_data
+    tr.clear_canvas()
+    tr.update_scene(sc.shapes, sc.triangles, sc.materials)
+    pixels = np.zeros(w * h * 4, np.uint8)
+    canvas = None
+    for tick in range(frames):
+        tr.options[:] = sc.render_data(tick)
+        tr.render(tick + 1, pixels)
+        canvas, _ = oracle_lib.render(tr.options, sc.scene_data, sc.shapes, sc.triangles, sc.materials, sky, canvas)
+    assert np.array_equal(got, pixels.reshape(h, w, 4)[..., 1:])
+    assert np.array_equal(got, oracle_lib.average(frames, canvas)[..., 1:])
