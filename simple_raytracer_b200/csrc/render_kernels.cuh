@@ -436,15 +436,27 @@ __device__ __forceinline__ void triangle_phase(const DevScene &sc, int n, int tr
 				if (lane == r) cand[q] = v;
 			}
 		}
-		if (active) {  // exact test of my ray's survivors, lowest triangle index first
+		if (active) {
+			// exact test of my ray's survivors, lowest triangle index first; ONE loop over all slots so the
+			// warp iterates max-over-lanes(total survivors) times, not once per slot
 #pragma unroll
-			for (int q = 0; q < TRIS_PER_LANE; ++q) {
-				uint32_t c = cand[q] & valid[q];
-				while (c) {
-					const int j = q * 32 + __ffs(c) - 1;
-					c &= c - 1;
-					tri_exact(tile[3 * j], tile[3 * j + 1], tile[3 * j + 2], o, d, shape, tri_begin + t * TILE_TRIS + j, hit);
-				}
+			for (int q = 0; q < TRIS_PER_LANE; ++q) cand[q] &= valid[q];
+			for (;;) {
+				int j = -1;
+#pragma unroll
+				for (int q = TRIS_PER_LANE - 1; q >= 0; --q)
+					if (cand[q]) j = q;
+				if (j < 0) break;
+				uint32_t c = 0;
+#pragma unroll
+				for (int q = 0; q < TRIS_PER_LANE; ++q)
+					if (q == j) c = cand[q];
+				const int bit = __ffs(c) - 1;
+#pragma unroll
+				for (int q = 0; q < TRIS_PER_LANE; ++q)
+					if (q == j) cand[q] = c & (c - 1);
+				j = j * 32 + bit;
+				tri_exact(tile[3 * j], tile[3 * j + 1], tile[3 * j + 2], o, d, shape, tri_begin + t * TILE_TRIS + j, hit);
 			}
 		}
 		__syncwarp();  // every lane is done reading this stage before it is refilled
