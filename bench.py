@@ -154,6 +154,8 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl cuda needs a GPU: the product has no CPU path")
     torch.cuda.set_device(local_rank)
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     sky = scenes.procedural_skybox()

@@ -12,7 +12,7 @@ from dataclasses import dataclass, field
 import numpy as np
 
 from .records import (MATERIAL, RENDER_DATA, SCENE_DATA, SHAPE, SHAPE_MODEL, SHAPE_PLANE,
-                      SHAPE_SPHERE, TRIANGLE)
+                      SHAPE_SPHERE, TRIANGLE, concat_records)  # noqa: F401
 
 F = np.float32
 

@@ -197,3 +197,96 @@ def test_shared_triangles_between_instances_and_empty_model(sky, oracle_lib):
     gi, gt = tr.debug_primary(rd)
     assert np.array_equal(oi, gi) and set(np.unique(gi)) >= {0, 1, 2, 4}
     assert_bit_equal(ot, gt, "t")
+
+
+def _random_mesh(rng, n_tris, center, extent):
+    """n_tris random (some degenerate, some huge, some sharing vertices/edges) triangles around `center`."""
+    base = rng.normal(size=(n_tris, 1, 3)) * extent * 0.6 + np.asarray(center)
+    pos = (base + rng.normal(size=(n_tris, 3, 3)) * extent * 0.35).astype(np.float32)
+    # shared edges / coplanar neighbours: triangle 2k+1 reuses two vertices of triangle 2k
+    pos[1::2, 0] = pos[0:n_tris - (n_tris % 2):2, 1][:len(pos[1::2])]
+    pos[1::2, 1] = pos[0:n_tris - (n_tris % 2):2, 2][:len(pos[1::2])]
+    if n_tris > 4:
+        pos[3, 2] = pos[3, 1]            # zero-area triangle
+        pos[4] = pos[2]                  # exact duplicate: equal t, the lower index must win
+    nrm = rng.normal(size=(n_tris, 3, 3)).astype(np.float32)
+    nrm /= np.linalg.norm(nrm, axis=-1, keepdims=True)
+    return scenes.triangles_from(pos, nrm)
+
+
+@pytest.mark.parametrize("sizes", [(33,), (127, 128, 129), (32, 257, 31, 1000, 64), (513, 40, 40, 40, 700, 33)])
+def test_models_of_awkward_sizes_tile_boundaries_and_many_instances(sky, oracle_lib, sizes):
+    """Triangle-phase bookkeeping: tile tails (n mod 128), the inline/parked threshold (32 / 33 triangles),
+    more distinct big models than a warp sweeps at once, duplicate and degenerate triangles, instances."""
+    rng = np.random.default_rng(sum(sizes))
+    tri_list, shapes = [], [scenes.plane(0, (0, -2.5, 0), (0, 1, 0)), scenes.sphere(1, (0, -1.0, -2.0), 0.8)]
+    first = 0
+    for i, n in enumerate(sizes):
+        ang = 2 * np.pi * i / len(sizes)
+        t = _random_mesh(rng, n, (2.2 * np.cos(ang), 0.4 * np.sin(3 * ang), -3.0 + 1.5 * np.sin(ang)), 1.0)
+        tri_list.append(t)
+        first += n
+    tris = scenes.concat_records(scenes.TRIANGLE, *tri_list) if hasattr(scenes, "concat_records") else None
+    if tris is None:
+        from simple_raytracer_b200.records import concat_records
+        tris = concat_records(scenes.TRIANGLE, *tri_list)
+    first = 0
+    for i, n in enumerate(sizes):
+        shapes.append(scenes.model(1 + i % 3, tris, first, n, scenes.rotate_y(0.1 * i)))
+        first += n
+    # a second instance of the first mesh, overlapping the others
+    shapes.append(scenes.model(2, tris, 0, sizes[0], scenes.translate((0.3, 0.2, 0.4)) @ scenes.scale(1.3)))
+    mats = scenes._stack([scenes.material((0.8, 0.8, 0.8)),
+                          scenes.material((0.9, 0.5, 0.3), smoothness=0.8, metallic=0.6),
+                          scenes.material((1, 1, 1), smoothness=1.0, transmittance=0.9, refraction_index=1.4),
+                          scenes.material((0.3, 0.6, 0.9), specular=0.4, smoothness=0.5)], scenes.MATERIAL)
+    sc = scenes.Scene("awkward", 192, 108, 2, 6, 2, scenes._stack(shapes, scenes.SHAPE), tris, mats,
+                      scenes.camera_matrix((0, 0.2, 3.5)))
+    tr = make_tracer(sc, sky)
+    rd = sc.render_data(0)
+    oi, ot = oracle_lib.primary(rd, sc.scene_data, sc.shapes, sc.triangles)
+    gi, gt = tr.debug_primary(rd)
+    assert np.array_equal(oi, gi)
+    assert_bit_equal(ot, gt, "t")
+    want, wcnt = None, None
+    tr.clear_canvas()
+    gcnt = None
+    for k in range(2):
+        rdk = sc.render_data(k)
+        want, c = oracle_lib.render(rdk, sc.scene_data, sc.shapes, sc.triangles, sc.materials, sky, want)
+        wcnt = [int(v) for v in c] if wcnt is None else [a + int(b) for a, b in zip(wcnt, c)]
+        gcnt = tr.accumulate_counted(rdk, gcnt)
+    assert_bit_equal(want, tr.read_canvas(), f"sizes {sizes} (counted kernel)")
+    assert wcnt == [int(gcnt[0][n]) for n in gcnt.dtype.names]
+    got = cuda_canvas(tr, sc, 2)
+    assert_bit_equal(want, got, f"sizes {sizes}")
+    assert len(set(np.unique(gi))) >= min(len(sizes), 3)
+
+
+def test_rays_through_shared_edges_and_vertices(sky, oracle_lib):
+    """Adversarial for the triangle filter: a regular grid of rays (time = 0 gives every pixel the same jitter)
+    against an axis-aligned triangle grid, so many rays pass within rounding distance of shared edges and
+    vertices (u, v near 0 or 1), plus the same grid seen almost edge-on (det near 0, grazing rays)."""
+    n = 24
+    xs = np.linspace(-1.5, 1.5, n + 1, dtype=np.float32)
+    X, Y = np.meshgrid(xs, xs, indexing="ij")
+    P = np.stack([X, Y, (-3.0 + 0.02 * np.sin(7 * X) * np.cos(5 * Y)).astype(np.float32)], -1)  # a flat AABB never passes (:289)
+    a, b, c, d = P[:-1, :-1], P[1:, :-1], P[:-1, 1:], P[1:, 1:]
+    pos = np.concatenate([np.stack([a, b, c], -2).reshape(-1, 3, 3), np.stack([b, d, c], -2).reshape(-1, 3, 3)])
+    nrm = np.tile(np.array([0, 0, 1], np.float32), (len(pos), 3, 1))
+    tris = scenes.triangles_from(pos, nrm)
+    edge_on = scenes.translate((0, 1e-4, -1.0)) @ scenes.rotate_x(np.pi / 2 - 1e-5) @ scenes.translate((0, 0, 3.0))
+    shapes = scenes._stack([scenes.model(0, tris, 0, len(tris), None),
+                            scenes.model(0, tris, 0, len(tris), edge_on)], scenes.SHAPE)
+    mats = scenes._stack([scenes.material((0.7, 0.7, 0.7), smoothness=0.3, specular=0.2)], scenes.MATERIAL)
+    sc = scenes.Scene("grid", 193, 193, 1, 3, 1, shapes, tris, mats, scenes.camera_matrix((0, 0, 0)))
+    tr = make_tracer(sc, sky)
+    rd = sc.render_data(0)
+    rd["time"] = 0  # time = 0 zeroes every seed: u0 = u1 = hash(0) for all pixels -> a regular grid of rays
+    oi, ot = oracle_lib.primary(rd, sc.scene_data, sc.shapes, sc.triangles)
+    gi, gt = tr.debug_primary(rd)
+    assert np.array_equal(oi, gi) and (gi == 0).sum() > 5000 and (gi == 1).sum() > 5000
+    assert_bit_equal(ot, gt, "t")
+    tr.accumulate(rd)
+    want, _ = oracle_lib.render(rd, sc.scene_data, sc.shapes, sc.triangles, sc.materials, sky)
+    assert_bit_equal(want, tr.read_canvas(), "grid")
