@@ -256,7 +256,7 @@ def main():
     except OSError:
         pass
     canvas_bytes = pixels * 32  # canvas RMW per launch: the only HBM-resident traffic of the kernel
-    roofline = {"bound": "fp32", "kernel": "srt::render_kernel<COUNT=false, MODELS=%s>" % ("true" if len(scene.triangles) else "false"), "achieved": achieved, "peak": peak_tf,
+    roofline = {"bound": "fp32", "kernel": "srt::render_kernel<COUNT=false, MODE=%s>" % ("BIG_MODELS" if len(scene.triangles) > 32 else ("SMALL_MODELS" if len(scene.triangles) else "ANALYTIC")), "achieved": achieved, "peak": peak_tf,
                 "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,
                 "peak_source": "FMA-chain micro-benchmark measured in this run (srt_measure_fp32_peak); "
                                f"nominal 148 SM x 128 x 2 x 1.965 GHz = {nominal:.1f}",

@@ -464,15 +464,20 @@ __device__ __forceinline__ void triangle_phase(const DevScene &sc, int n, int tr
 	}
 }
 
-// MODELS = false is the build for scenes without any model shape: no triangle code, no shared memory,
-// fewer registers (more resident warps for the latency-bound analytic path).
-template <bool COUNT, bool MODELS>
-__global__ void __launch_bounds__(RENDER_THREADS, MODELS ? SRT_MIN_BLOCKS : SRT_MIN_BLOCKS_ANALYTIC)
+// MODE selects the build: MODE_ANALYTIC for scenes without any model shape (no triangle code at all),
+// MODE_SMALL_MODELS when every model is small enough to be intersected inline during the scan (no
+// parking, no shared memory), MODE_BIG_MODELS for the full machine.  The first two need fewer registers,
+// i.e. more resident warps for the latency-bound analytic path.
+enum { MODE_ANALYTIC = 0, MODE_SMALL_MODELS = 1, MODE_BIG_MODELS = 2 };
+template <bool COUNT, int MODE>
+__global__ void __launch_bounds__(RENDER_THREADS, MODE == MODE_BIG_MODELS ? SRT_MIN_BLOCKS : SRT_MIN_BLOCKS_ANALYTIC)
 render_kernel(const __grid_constant__ RenderParams p, const __grid_constant__ DevScene sc,
               float4 *__restrict__ canvas, unsigned int *__restrict__ cursor, Counters *__restrict__ counters) {
 	const unsigned FULL = 0xffffffffu;
 	const int lane = threadIdx.x & 31;
 	Counters cnt = {0, 0, 0, 0, 0, 0};
+	constexpr bool MODELS = MODE != MODE_ANALYTIC;   // the scan knows about model shapes
+	constexpr bool PHASES = MODE == MODE_BIG_MODELS;  // lanes park and the warp runs dense triangle phases
 
 	// per-warp ring of triangle tiles + one mbarrier per stage
 	extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -481,7 +486,7 @@ render_kernel(const __grid_constant__ RenderParams p, const __grid_constant__ De
 	const uint32_t wsmem_s = smem_u32(wsmem);
 	const uint32_t bars_s = smem_u32(smem_raw + RENDER_WARPS * WARP_SMEM_BYTES + warp * (TILE_STAGES * 8));
 	uint32_t parity = 0;
-	if (MODELS) {
+	if (PHASES) {
 		if (lane == 0) {
 			for (int st = 0; st < TILE_STAGES; ++st) mbar_init(bars_s + st * 8, 1);
 			asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -562,7 +567,7 @@ render_kernel(const __grid_constant__ RenderParams p, const __grid_constant__ De
 				if (MODELS) inv = mk(div_(1.0f, d.x), div_(1.0f, d.y), div_(1.0f, d.z));
 				scan_at = 0;
 			}
-			park = scan_shapes<COUNT, true, MODELS>(sc, o, d, inv, scan_at, hit, cnt);
+			park = scan_shapes<COUNT, PHASES, MODELS>(sc, o, d, inv, scan_at, hit, cnt);
 
 			if (park < 0) {  // scan complete: shade this bounce, :404-468
 				scan_at = -1;
@@ -606,8 +611,8 @@ render_kernel(const __grid_constant__ RenderParams p, const __grid_constant__ De
 		// -- dense triangle phase.  Lane utilisation inside the phase does not depend on how many rays are
 		// parked (the lanes hold triangles there), so it runs after at most PHASE_PATIENCE trips of waiting
 		// for company; parked lanes get back to tracing as soon as possible.
-		const unsigned parked = MODELS ? __ballot_sync(FULL, park >= 0) : 0u;
-		if (MODELS && parked) {
+		const unsigned parked = PHASES ? __ballot_sync(FULL, park >= 0) : 0u;
+		if (PHASES && parked) {
 			const unsigned movable = __ballot_sync(FULL, alive && park < 0);
 			if (movable == 0 || waited >= PHASE_PATIENCE) {
 				// the model most lanes wait for (ties: the lower shape index)

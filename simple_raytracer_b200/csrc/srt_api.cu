@@ -76,12 +76,12 @@ struct srt_tracer {
 	DevBuf<float4> tri_aos, tri_hot, tri_n;
 	DevBuf<srt::ModelSpan> spans;
 	size_t n_shapes = 0, n_materials = 0, n_soa_tris = 0;
-	bool has_models = false;
+	bool has_models = false, has_big_models = false;
 	srt_scene_data scene_data{};
 	bool have_scene = false;
 
 	int band_h = 1, band_i = 0, band_n = 1;
-	int render_grid[2][2] = {{0, 0}, {0, 0}};  // [counted][models]
+	int render_grid[2][3] = {{0, 0, 0}, {0, 0, 0}};  // [counted][mode]
 
 	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing;  // render launches since last query
 	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> event_pool;
@@ -167,11 +167,11 @@ int make_params(srt_tracer *t, const srt_render_data *rd, srt::RenderParams &p) 
 	return SRT_OK;
 }
 
-template <bool COUNT, bool MODELS>
+template <bool COUNT, int MODE>
 int launch_render_impl(srt_tracer *t, const srt::RenderParams &p) {
-	auto kernel = srt::render_kernel<COUNT, MODELS>;
-	const int smem = MODELS ? srt::RENDER_SMEM_BYTES : 0;
-	int &grid = t->render_grid[COUNT ? 1 : 0][MODELS ? 1 : 0];
+	auto kernel = srt::render_kernel<COUNT, MODE>;
+	const int smem = MODE == srt::MODE_BIG_MODELS ? srt::RENDER_SMEM_BYTES : 0;
+	int &grid = t->render_grid[COUNT ? 1 : 0][MODE];
 	if (grid == 0) {
 		int per_sm = 0;
 		if (smem) SRT_CUDA(t, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -205,7 +205,9 @@ int launch_render(srt_tracer *t, const srt_render_data *rd) {
 	srt::RenderParams p{};
 	if (int rc = make_params(t, rd, p)) return rc;
 	if (p.num_bounces == 0 || p.total_items == 0) return SRT_OK;  // render.cl:403: zero bounces add zero radiance
-	return t->has_models ? launch_render_impl<COUNT, true>(t, p) : launch_render_impl<COUNT, false>(t, p);
+	if (!t->has_models) return launch_render_impl<COUNT, srt::MODE_ANALYTIC>(t, p);
+	if (!t->has_big_models) return launch_render_impl<COUNT, srt::MODE_SMALL_MODELS>(t, p);
+	return launch_render_impl<COUNT, srt::MODE_BIG_MODELS>(t, p);
 }
 
 }  // namespace
@@ -366,6 +368,7 @@ int srt_upload_scene(srt_tracer *t, const srt_shape *shapes, size_t n_shapes, co
 	t->n_shapes = n_shapes;
 	t->n_materials = n_materials;
 	t->n_soa_tris = soa;
+	t->has_big_models = std::any_of(hdr.begin(), hdr.end(), [](const int4 &h) { return h.x == SRT_SHAPE_MODEL && h.w > srt::INLINE_MODEL_TRIS; });
 	t->has_models = soa > 0 || std::any_of(hdr.begin(), hdr.end(), [](const int4 &h) { return h.x == SRT_SHAPE_MODEL; });
 	t->scene_data = *scene_data;
 	t->scene_data.num_shapes = (int)n_shapes;  // tracer.cpp:94
