@@ -3,13 +3,13 @@
 // Replaces the OpenCL kernels `render` and `average` of reference src/render.cl:483-535 (and every
 // helper they call, :114-481).  This is not a translation of that file: the device data is SoA with
 // model triangles pre-transformed to world space (v0, e1, e2) at upload, path state lives in
-// registers, and the bounce loop is FLATTENED -- one persistent thread owns a stream of
-// (pixel, sample) paths and runs exactly one bounce per loop trip, regenerating the next camera
-// path in place the moment its current path ends.  A warp therefore never waits on its longest path:
-// terminated lanes are refilled through a ballot-aggregated atomic on a global pixel cursor, and
-// warps stay full until the frame runs dry.  Per-pixel sample order (render.cl:495-520) is kept
-// because a lane owns all num_samples paths of its pixel, so results are bit-identical to the
-// sequential formulation.
+// registers, and the bounce loop is FLATTENED -- one persistent thread pulls (pixel, sample) work
+// items and runs exactly one bounce per loop trip, starting the next camera path in place the moment
+// its current path ends.  A warp therefore never waits on its longest path: terminated lanes are
+// refilled through a ballot-aggregated atomic on a global item cursor, and warps stay full until the
+// frame runs dry.  Every path writes its radiance to a per-launch scratch buffer; accumulate_kernel
+// then adds the samples of each pixel in sample order (render.cl:495-522), so results are bit-identical
+// to the sequential formulation while the unit of scheduling is one path, not one pixel.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -47,7 +47,8 @@ struct RenderParams {
 	// row-band tiling (srt_set_row_bands)
 	int band_h, band_i, band_n;
 	int my_rows;               // number of rows this launch renders
-	unsigned int total_items;  // my_rows * width
+	unsigned int total_pixels; // my_rows * width
+	unsigned int total_items;  // total_pixels * num_samples: item = local_pixel * num_samples + sample
 	float inv_ns;              // 1/num_samples when that is exact (num_samples a power of two), else 0
 };
 
@@ -472,7 +473,7 @@ enum { MODE_ANALYTIC = 0, MODE_SMALL_MODELS = 1, MODE_BIG_MODELS = 2 };
 template <bool COUNT, int MODE>
 __global__ void __launch_bounds__(RENDER_THREADS, MODE == MODE_BIG_MODELS ? SRT_MIN_BLOCKS : SRT_MIN_BLOCKS_ANALYTIC)
 render_kernel(const __grid_constant__ RenderParams p, const __grid_constant__ DevScene sc,
-              float4 *__restrict__ canvas, unsigned int *__restrict__ cursor, Counters *__restrict__ counters) {
+              float4 *__restrict__ scratch, unsigned int *__restrict__ cursor, Counters *__restrict__ counters) {
 	const unsigned FULL = 0xffffffffu;
 	const int lane = threadIdx.x & 31;
 	Counters cnt = {0, 0, 0, 0, 0, 0};
@@ -495,70 +496,51 @@ render_kernel(const __grid_constant__ RenderParams p, const __grid_constant__ De
 	}
 
 	bool alive = true;
-	int pix = -1, gx = 0, gy = 0;
-	int sample = p.num_samples;  // forces a pixel fetch on the first trip
+	bool fresh = true;  // the lane needs a new work item (and a camera ray)
+	unsigned int item = 0;
 	int bounce = 0;
-	bool fresh = false;          // a camera ray must be generated
 	uint32_t seed = 0;
-	vec3 o = mk(0, 0, 0), d = mk(0, 0, 1), mask = mk(1, 1, 1), color = mk(0, 0, 0), pixsum = mk(0, 0, 0);
+	vec3 o = mk(0, 0, 0), d = mk(0, 0, 1), mask = mk(1, 1, 1), color = mk(0, 0, 0);
 	// closest-hit scan state of the current bounce
 	vec3 inv = mk(0, 0, 0);
 	Hit hit = {0.f, -1, -1};
 	int scan_at = -1;  // next shape to visit; -1 = a new bounce has to be started
 	int park = -1;     // shape index of the model this lane waits to run triangles for
 	int waited = 0;    // warp-uniform: trips spent with parked lanes waiting for company
-	const float ns_f = (float)p.num_samples;
 
 	for (;;) {
-		// -- refill: lanes whose pixel is complete commit it and pull the next pixel id
-		const bool need_pixel = alive && sample == p.num_samples;
-		const unsigned need = __ballot_sync(FULL, need_pixel);
+		// -- refill: lanes whose path ended pull the next (pixel, sample) item and start its camera path
+		const bool need_item = alive && fresh;
+		const unsigned need = __ballot_sync(FULL, need_item);
 		if (need) {
 			unsigned int base = 0;
 			if (lane == 0) base = atomicAdd(cursor, (unsigned int)__popc(need));
 			base = __shfl_sync(FULL, base, 0);
-			if (need_pixel) {
-				if (pix >= 0) {  // canvas[id] += color / num_samples, :520-522
-					float4 c = canvas[pix];
-					if (p.inv_ns != 0.0f) {  // x / 2^k == x * 2^-k exactly
-						c.x += pixsum.x * p.inv_ns;
-						c.y += pixsum.y * p.inv_ns;
-						c.z += pixsum.z * p.inv_ns;
-					} else {
-						c.x += div_(pixsum.x, ns_f);
-						c.y += div_(pixsum.y, ns_f);
-						c.z += div_(pixsum.z, ns_f);
-					}
-					canvas[pix] = c;
-				}
-				const unsigned int item = base + __popc(need & ((1u << lane) - 1u));
-				if (item < p.total_items) {
-					int row = (int)(item / (unsigned)p.width);
-					gx = (int)(item - (unsigned)row * (unsigned)p.width);
-					gy = p.band_n > 1 ? ((row / p.band_h) * p.band_n + p.band_i) * p.band_h + (row % p.band_h) : row;
-					pix = gx + gy * p.width;
-					sample = 0;
-					pixsum = mk(0, 0, 0);
-					fresh = true;
+			if (need_item) {
+				item = base + __popc(need & ((1u << lane) - 1u));
+				if (item < p.total_items) {  // start path `sample` of pixel `pix`, :496-516
+					const unsigned int lp = item / (unsigned)p.num_samples;  // local pixel
+					const unsigned int sample = item - lp * (unsigned)p.num_samples;
+					const int row = (int)(lp / (unsigned)p.width);
+					const int gx = (int)(lp - (unsigned)row * (unsigned)p.width);
+					const int gy = p.band_n > 1 ? ((row / p.band_h) * p.band_n + p.band_i) * p.band_h + (row % p.band_h) : row;
+					const uint32_t pix = (uint32_t)gx + (uint32_t)gy * (uint32_t)p.width;
+					seed = (sample + pix * (uint32_t)p.num_samples) * p.time * 5304u;
+					camera_ray(p, gx, gy, seed, o, d);
+					mask = mk(1, 1, 1);
+					color = mk(0, 0, 0);
+					bounce = 0;
+					fresh = false;
+					scan_at = -1;
+					if (COUNT) cnt.samples += 1;
 				} else {
 					alive = false;
-					pix = -1;
 				}
 			}
 		}
 		if (!__any_sync(FULL, alive)) break;
 
 		if (alive && park < 0) {
-			if (fresh) {  // start path `sample` of pixel `pix`, :496-516
-				seed = ((uint32_t)sample + (uint32_t)pix * (uint32_t)p.num_samples) * p.time * 5304u;
-				camera_ray(p, gx, gy, seed, o, d);
-				mask = mk(1, 1, 1);
-				color = mk(0, 0, 0);
-				bounce = 0;
-				fresh = false;
-				scan_at = -1;
-				if (COUNT) cnt.samples += 1;
-			}
 			if (scan_at < 0) {  // new bounce: closest_intersection prologue, :294-297
 				if (COUNT) cnt.bounces += 1;
 				hit.t = __int_as_float(0x7f800000);
@@ -600,9 +582,8 @@ render_kernel(const __grid_constant__ RenderParams p, const __grid_constant__ De
 					color = color + mask;
 					done = true;
 				}
-				if (done) {
-					pixsum = pixsum + color;  // :518
-					sample += 1;
+				if (done) {  // the sample's radiance; accumulate_kernel sums a pixel's samples in order (:518-522)
+					scratch[item] = make_float4(color.x, color.y, color.z, 0.f);
 					fresh = true;
 				}
 			}
@@ -642,6 +623,29 @@ render_kernel(const __grid_constant__ RenderParams p, const __grid_constant__ De
 			if (lane == 0 && v) atomicAdd(reinterpret_cast<unsigned long long *>(counters) + k, v);
 		}
 	}
+}
+
+// ---- per-launch epilogue of `render`: color = sum of the pixel's samples in sample order (:494-519),
+// color /= num_samples (:520), canvas[id] += color (:522).  One thread per local pixel.
+__global__ void __launch_bounds__(256)
+accumulate_kernel(const __grid_constant__ RenderParams p, const float4 *__restrict__ scratch, float4 *__restrict__ canvas) {
+	const unsigned int lp = blockIdx.x * blockDim.x + threadIdx.x;
+	if (lp >= p.total_pixels) return;
+	const float4 *s = scratch + (size_t)lp * p.num_samples;
+	vec3 color = mk(0, 0, 0);
+	for (int k = 0; k < p.num_samples; ++k) color = color + xyz(s[k]);
+	const int row = (int)(lp / (unsigned)p.width);
+	const int gx = (int)(lp - (unsigned)row * (unsigned)p.width);
+	const int gy = p.band_n > 1 ? ((row / p.band_h) * p.band_n + p.band_i) * p.band_h + (row % p.band_h) : row;
+	const size_t pix = (size_t)gx + (size_t)gy * p.width;
+	float4 c = canvas[pix];
+	if (p.inv_ns != 0.0f) {  // x / 2^k == x * 2^-k exactly
+		c.x += color.x * p.inv_ns, c.y += color.y * p.inv_ns, c.z += color.z * p.inv_ns;
+	} else {
+		const float ns_f = (float)p.num_samples;
+		c.x += div_(color.x, ns_f), c.y += div_(color.y, ns_f), c.z += div_(color.z, ns_f);
+	}
+	canvas[pix] = c;
 }
 
 // ---- kernel `average`, render.cl:525-535 (aces :473-481) ---------------------------------------

@@ -74,6 +74,7 @@ struct srt_tracer {
 	DevBuf<int4> shape_hdr;
 	DevBuf<float4> shape_a, shape_b, model_xf, materials;
 	DevBuf<float4> tri_aos, tri_hot, tri_n;
+	DevBuf<float4> scratch;  // one float4 per (pixel, sample) of a launch
 	DevBuf<srt::ModelSpan> spans;
 	size_t n_shapes = 0, n_materials = 0, n_soa_tris = 0;
 	bool has_models = false, has_big_models = false;
@@ -163,7 +164,10 @@ int make_params(srt_tracer *t, const srt_render_data *rd, srt::RenderParams &p) 
 			if ((y / t->band_h) % t->band_n == t->band_i) ++rows;
 	}
 	p.my_rows = rows;
-	p.total_items = (unsigned int)rows * (unsigned int)rd->width;
+	p.total_pixels = (unsigned int)rows * (unsigned int)rd->width;
+	if ((unsigned long long)p.total_pixels * (unsigned long long)rd->num_samples > 0xfffffff0ull)
+		return fail(t, SRT_ERR_INVALID, "width*height*num_samples exceeds 2^32 work items per launch");
+	p.total_items = p.total_pixels * (unsigned int)rd->num_samples;
 	return SRT_OK;
 }
 
@@ -188,8 +192,10 @@ int launch_render_impl(srt_tracer *t, const srt::RenderParams &p) {
 		SRT_CUDA(t, cudaEventCreate(&ev.second));
 	}
 	const srt::DevScene sc = dev_scene(t);
+	SRT_CUDA(t, t->scratch.reserve(p.total_items));
 	SRT_CUDA(t, cudaEventRecord(ev.first, t->stream));
-	kernel<<<grid, srt::RENDER_THREADS, smem, t->stream>>>(p, sc, t->canvas, t->cursor, t->counters);
+	kernel<<<grid, srt::RENDER_THREADS, smem, t->stream>>>(p, sc, t->scratch.ptr, t->cursor, t->counters);
+	srt::accumulate_kernel<<<(p.total_pixels + 255) / 256, 256, 0, t->stream>>>(p, t->scratch.ptr, t->canvas);
 	SRT_CUDA(t, cudaEventRecord(ev.second, t->stream));
 	SRT_CUDA(t, cudaGetLastError());
 	if (t->timing.size() >= 4096) {  // nobody is reading the timings: recycle
@@ -286,7 +292,7 @@ int srt_destroy(srt_tracer *t) {
 	cudaFree(t->counters);
 	cudaFree(t->sky);
 	t->shape_hdr.release(), t->shape_a.release(), t->shape_b.release(), t->model_xf.release(), t->materials.release();
-	t->tri_aos.release(), t->tri_hot.release(), t->tri_n.release(), t->spans.release();
+	t->tri_aos.release(), t->tri_hot.release(), t->tri_n.release(), t->spans.release(), t->scratch.release();
 	if (t->stream) cudaStreamDestroy(t->stream);
 	delete t;
 	return SRT_OK;
