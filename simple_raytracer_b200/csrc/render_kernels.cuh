@@ -465,6 +465,30 @@ __device__ __forceinline__ void triangle_phase(const DevScene &sc, int n, int tr
 	}
 }
 
+// Start the camera path of work item `item` = local_pixel * num_samples + sample (render.cl:488-516).
+__device__ __forceinline__ void start_path(const RenderParams &p, unsigned int item, uint32_t &seed, vec3 &o, vec3 &d) {
+	const unsigned int lp = item / (unsigned)p.num_samples;  // local pixel
+	const unsigned int sample = item - lp * (unsigned)p.num_samples;
+	const int row = (int)(lp / (unsigned)p.width);
+	const int gx = (int)(lp - (unsigned)row * (unsigned)p.width);
+	const int gy = p.band_n > 1 ? ((row / p.band_h) * p.band_n + p.band_i) * p.band_h + (row % p.band_h) : row;
+	const uint32_t pix = (uint32_t)gx + (uint32_t)gy * (uint32_t)p.width;
+	seed = (sample + pix * (uint32_t)p.num_samples) * p.time * 5304u;
+	camera_ray(p, gx, gy, seed, o, d);
+}
+
+// Per-warp shared-memory queues of the analytic builds (MODE_ANALYTIC, MODE_SMALL_MODELS).
+// The two things only a minority of lanes needs in any one trip -- a fresh camera path (about one lane in five)
+// and a sky-box evaluation (paths that just escaped) -- are not executed by that minority under divergence:
+// camera paths are generated 32 at a time into a ring the finishing lanes pop from, and escaped paths push
+// {item, radiance, throughput, direction} into a ring that is evaluated 32 at a time.  Both run with all lanes
+// active.  Results go to scratch[item], so the order in which records are flushed does not matter.
+constexpr int QUEUE_SLOTS = 64;  // < 32 left over + <= 32 pushed per trip
+constexpr int RAYQ_WORDS = 5;    // item, seed, d.xyz          (origin = camera position)
+constexpr int SKYQ_WORDS = 10;   // item, color.xyz, mask.xyz, d.xyz
+constexpr int QUEUE_WARP_BYTES = (RAYQ_WORDS + SKYQ_WORDS) * QUEUE_SLOTS * 4;
+constexpr int QUEUE_SMEM_BYTES = (SRT_RENDER_THREADS / 32) * QUEUE_WARP_BYTES;
+
 // MODE selects the build: MODE_ANALYTIC for scenes without any model shape (no triangle code at all),
 // MODE_SMALL_MODELS when every model is small enough to be intersected inline during the scan (no
 // parking, no shared memory), MODE_BIG_MODELS for the full machine.  The first two need fewer registers,
@@ -479,6 +503,7 @@ render_kernel(const __grid_constant__ RenderParams p, const __grid_constant__ De
 	Counters cnt = {0, 0, 0, 0, 0, 0};
 	constexpr bool MODELS = MODE != MODE_ANALYTIC;   // the scan knows about model shapes
 	constexpr bool PHASES = MODE == MODE_BIG_MODELS;  // lanes park and the warp runs dense triangle phases
+	constexpr bool QUEUES = !PHASES;                  // dense camera-path / sky-box batches through warp queues
 
 	// per-warp ring of triangle tiles + one mbarrier per stage
 	extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -507,12 +532,84 @@ render_kernel(const __grid_constant__ RenderParams p, const __grid_constant__ De
 	int scan_at = -1;  // next shape to visit; -1 = a new bounce has to be started
 	int park = -1;     // shape index of the model this lane waits to run triangles for
 	int waited = 0;    // warp-uniform: trips spent with parked lanes waiting for company
+	// warp-uniform queue state (QUEUES builds)
+	uint32_t *rayq = reinterpret_cast<uint32_t *>(smem_raw + warp * QUEUE_WARP_BYTES);
+	float *skyq = reinterpret_cast<float *>(rayq + RAYQ_WORDS * QUEUE_SLOTS);
+	int ray_head = 0, ray_count = 0, sky_head = 0, sky_count = 0;
+	bool exhausted = false;
+	const unsigned lt_mask = (1u << lane) - 1u;
+	const vec3 cam_origin = mk(p.c2w[12], p.c2w[13], p.c2w[14]);
+
+	// evaluate `n` queued sky records (n <= 32), one per lane: mask *= sky, color += mask (:464-465)
+	auto flush_sky = [&](int n) {
+		if (lane < n) {
+			const int sl = (sky_head + lane) & (QUEUE_SLOTS - 1);
+			const unsigned int it = __float_as_uint(skyq[0 * QUEUE_SLOTS + sl]);
+			const vec3 c = mk(skyq[1 * QUEUE_SLOTS + sl], skyq[2 * QUEUE_SLOTS + sl], skyq[3 * QUEUE_SLOTS + sl]);
+			vec3 m = mk(skyq[4 * QUEUE_SLOTS + sl], skyq[5 * QUEUE_SLOTS + sl], skyq[6 * QUEUE_SLOTS + sl]);
+			const vec3 dir = mk(skyq[7 * QUEUE_SLOTS + sl], skyq[8 * QUEUE_SLOTS + sl], skyq[9 * QUEUE_SLOTS + sl]);
+			m = m * sky_box(sc, dir);
+			const vec3 r = c + m;
+			scratch[it] = make_float4(r.x, r.y, r.z, 0.f);
+		}
+		sky_head = (sky_head + n) & (QUEUE_SLOTS - 1);
+		sky_count -= n;
+		__syncwarp();
+	};
 
 	for (;;) {
 		// -- refill: lanes whose path ended pull the next (pixel, sample) item and start its camera path
 		const bool need_item = alive && fresh;
 		const unsigned need = __ballot_sync(FULL, need_item);
-		if (need) {
+		if (QUEUES && need) {
+			const int want = __popc(need);
+			if (ray_count < want && !exhausted) {  // generate 32 camera paths with every lane active
+				unsigned int base = 0;
+				if (lane == 0) base = atomicAdd(cursor, 32u);
+				base = __shfl_sync(FULL, base, 0);
+				const unsigned int it = base + lane;
+				const bool valid = it < p.total_items;
+				const unsigned vm = __ballot_sync(FULL, valid);
+				if (valid) {
+					uint32_t sd;
+					vec3 oo, dd;
+					start_path(p, it, sd, oo, dd);
+					const int sl = (ray_head + ray_count + __popc(vm & lt_mask)) & (QUEUE_SLOTS - 1);
+					rayq[0 * QUEUE_SLOTS + sl] = it;
+					rayq[1 * QUEUE_SLOTS + sl] = sd;
+					rayq[2 * QUEUE_SLOTS + sl] = __float_as_uint(dd.x);
+					rayq[3 * QUEUE_SLOTS + sl] = __float_as_uint(dd.y);
+					rayq[4 * QUEUE_SLOTS + sl] = __float_as_uint(dd.z);
+					if (COUNT) cnt.samples += 1;
+				}
+				ray_count += __popc(vm);
+				exhausted = vm != FULL;
+				__syncwarp();
+			}
+			if (need_item) {
+				const int r = __popc(need & lt_mask);
+				if (r < ray_count) {
+					const int sl = (ray_head + r) & (QUEUE_SLOTS - 1);
+					item = rayq[0 * QUEUE_SLOTS + sl];
+					seed = rayq[1 * QUEUE_SLOTS + sl];
+					d = mk(__uint_as_float(rayq[2 * QUEUE_SLOTS + sl]), __uint_as_float(rayq[3 * QUEUE_SLOTS + sl]),
+					       __uint_as_float(rayq[4 * QUEUE_SLOTS + sl]));
+					o = cam_origin;
+					mask = mk(1, 1, 1);
+					color = mk(0, 0, 0);
+					bounce = 0;
+					fresh = false;
+					scan_at = -1;
+				} else {
+					alive = false;  // the frame has run dry
+				}
+			}
+			const int popped = min(want, ray_count);
+			ray_head = (ray_head + popped) & (QUEUE_SLOTS - 1);
+			ray_count -= popped;
+			__syncwarp();
+		}
+		if (!QUEUES && need) {
 			unsigned int base = 0;
 			if (lane == 0) base = atomicAdd(cursor, (unsigned int)__popc(need));
 			base = __shfl_sync(FULL, base, 0);
@@ -540,6 +637,7 @@ render_kernel(const __grid_constant__ RenderParams p, const __grid_constant__ De
 		}
 		if (!__any_sync(FULL, alive)) break;
 
+		bool push_sky = false;
 		if (alive && park < 0) {
 			if (scan_at < 0) {  // new bounce: closest_intersection prologue, :294-297
 				if (COUNT) cnt.bounces += 1;
@@ -578,14 +676,36 @@ render_kernel(const __grid_constant__ RenderParams p, const __grid_constant__ De
 					}
 				} else {  // :463-467
 					if (COUNT) cnt.sky += 1;
-					mask = mask * sky_box(sc, d);
-					color = color + mask;
-					done = true;
+					if (QUEUES) {
+						push_sky = true;  // evaluated 32 at a time below
+						fresh = true;
+						done = false;
+					} else {
+						mask = mask * sky_box(sc, d);
+						color = color + mask;
+						done = true;
+					}
 				}
 				if (done) {  // the sample's radiance; accumulate_kernel sums a pixel's samples in order (:518-522)
 					scratch[item] = make_float4(color.x, color.y, color.z, 0.f);
 					fresh = true;
 				}
+			}
+		}
+
+		if (QUEUES) {  // escaped paths: queue {item, color, mask, direction}; evaluate the sky box 32 at a time
+			const unsigned sm = __ballot_sync(FULL, push_sky);
+			if (sm) {
+				if (push_sky) {
+					const int sl = (sky_head + sky_count + __popc(sm & lt_mask)) & (QUEUE_SLOTS - 1);
+					skyq[0 * QUEUE_SLOTS + sl] = __uint_as_float(item);
+					skyq[1 * QUEUE_SLOTS + sl] = color.x, skyq[2 * QUEUE_SLOTS + sl] = color.y, skyq[3 * QUEUE_SLOTS + sl] = color.z;
+					skyq[4 * QUEUE_SLOTS + sl] = mask.x, skyq[5 * QUEUE_SLOTS + sl] = mask.y, skyq[6 * QUEUE_SLOTS + sl] = mask.z;
+					skyq[7 * QUEUE_SLOTS + sl] = d.x, skyq[8 * QUEUE_SLOTS + sl] = d.y, skyq[9 * QUEUE_SLOTS + sl] = d.z;
+				}
+				sky_count += __popc(sm);
+				__syncwarp();
+				if (sky_count >= 32) flush_sky(32);
 			}
 		}
 
@@ -614,6 +734,8 @@ render_kernel(const __grid_constant__ RenderParams p, const __grid_constant__ De
 			}
 		}
 	}
+
+	if (QUEUES && sky_count > 0) flush_sky(sky_count);
 
 	if (COUNT) {
 		unsigned long long *c = reinterpret_cast<unsigned long long *>(&cnt);

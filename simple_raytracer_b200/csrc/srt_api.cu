@@ -174,7 +174,7 @@ int make_params(srt_tracer *t, const srt_render_data *rd, srt::RenderParams &p) 
 template <bool COUNT, int MODE>
 int launch_render_impl(srt_tracer *t, const srt::RenderParams &p) {
 	auto kernel = srt::render_kernel<COUNT, MODE>;
-	const int smem = MODE == srt::MODE_BIG_MODELS ? srt::RENDER_SMEM_BYTES : 0;
+	const int smem = MODE == srt::MODE_BIG_MODELS ? srt::RENDER_SMEM_BYTES : srt::QUEUE_SMEM_BYTES;
 	int &grid = t->render_grid[COUNT ? 1 : 0][MODE];
 	if (grid == 0) {
 		int per_sm = 0;
