@@ -483,11 +483,15 @@ __device__ __forceinline__ void start_path(const RenderParams &p, unsigned int i
 // camera paths are generated 32 at a time into a ring the finishing lanes pop from, and escaped paths push
 // {item, radiance, throughput, direction} into a ring that is evaluated 32 at a time.  Both run with all lanes
 // active.  Results go to scratch[item], so the order in which records are flushed does not matter.
+#ifndef SRT_BIG_SKYQ
+#define SRT_BIG_SKYQ 0
+#endif
 constexpr int QUEUE_SLOTS = 64;  // < 32 left over + <= 32 pushed per trip
 constexpr int RAYQ_WORDS = 5;    // item, seed, d.xyz          (origin = camera position)
 constexpr int SKYQ_WORDS = 10;   // item, color.xyz, mask.xyz, d.xyz
 constexpr int QUEUE_WARP_BYTES = (RAYQ_WORDS + SKYQ_WORDS) * QUEUE_SLOTS * 4;
 constexpr int QUEUE_SMEM_BYTES = (SRT_RENDER_THREADS / 32) * QUEUE_WARP_BYTES;
+constexpr int BIG_SKYQ_BYTES = SRT_BIG_SKYQ ? (SRT_RENDER_THREADS / 32) * SKYQ_WORDS * QUEUE_SLOTS * 4 : 0;
 
 // MODE selects the build: MODE_ANALYTIC for scenes without any model shape (no triangle code at all),
 // MODE_SMALL_MODELS when every model is small enough to be intersected inline during the scan (no
@@ -503,7 +507,8 @@ render_kernel(const __grid_constant__ RenderParams p, const __grid_constant__ De
 	Counters cnt = {0, 0, 0, 0, 0, 0};
 	constexpr bool MODELS = MODE != MODE_ANALYTIC;   // the scan knows about model shapes
 	constexpr bool PHASES = MODE == MODE_BIG_MODELS;  // lanes park and the warp runs dense triangle phases
-	constexpr bool QUEUES = !PHASES;                  // dense camera-path / sky-box batches through warp queues
+	constexpr bool QUEUES = !PHASES;                  // dense camera-path batches through a warp queue
+	constexpr bool SKYQ = QUEUES || SRT_BIG_SKYQ;     // dense sky-box batches through a warp queue
 
 	// per-warp ring of triangle tiles + one mbarrier per stage
 	extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -534,7 +539,8 @@ render_kernel(const __grid_constant__ RenderParams p, const __grid_constant__ De
 	int waited = 0;    // warp-uniform: trips spent with parked lanes waiting for company
 	// warp-uniform queue state (QUEUES builds)
 	uint32_t *rayq = reinterpret_cast<uint32_t *>(smem_raw + warp * QUEUE_WARP_BYTES);
-	float *skyq = reinterpret_cast<float *>(rayq + RAYQ_WORDS * QUEUE_SLOTS);
+	float *skyq = PHASES ? reinterpret_cast<float *>(smem_raw + RENDER_SMEM_BYTES + warp * (SKYQ_WORDS * QUEUE_SLOTS * 4))
+	                     : reinterpret_cast<float *>(rayq + RAYQ_WORDS * QUEUE_SLOTS);
 	int ray_head = 0, ray_count = 0, sky_head = 0, sky_count = 0;
 	bool exhausted = false;
 	const unsigned lt_mask = (1u << lane) - 1u;
@@ -676,7 +682,7 @@ render_kernel(const __grid_constant__ RenderParams p, const __grid_constant__ De
 					}
 				} else {  // :463-467
 					if (COUNT) cnt.sky += 1;
-					if (QUEUES) {
+					if (SKYQ) {
 						push_sky = true;  // evaluated 32 at a time below
 						fresh = true;
 						done = false;
@@ -693,7 +699,7 @@ render_kernel(const __grid_constant__ RenderParams p, const __grid_constant__ De
 			}
 		}
 
-		if (QUEUES) {  // escaped paths: queue {item, color, mask, direction}; evaluate the sky box 32 at a time
+		if (SKYQ) {  // escaped paths: queue {item, color, mask, direction}; evaluate the sky box 32 at a time
 			const unsigned sm = __ballot_sync(FULL, push_sky);
 			if (sm) {
 				if (push_sky) {
@@ -735,7 +741,7 @@ render_kernel(const __grid_constant__ RenderParams p, const __grid_constant__ De
 		}
 	}
 
-	if (QUEUES && sky_count > 0) flush_sky(sky_count);
+	if (SKYQ && sky_count > 0) flush_sky(sky_count);
 
 	if (COUNT) {
 		unsigned long long *c = reinterpret_cast<unsigned long long *>(&cnt);

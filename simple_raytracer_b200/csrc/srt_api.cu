@@ -66,6 +66,8 @@ struct srt_tracer {
 	float4 *canvas = nullptr;  // float3 with 16-byte stride (tracer.cpp:39)
 	uchar4 *output = nullptr;  // ARGB8 (tracer.cpp:40)
 	uint8_t *pinned_out = nullptr;
+	void *registered_out = nullptr;  // caller's output vector, page-locked once it is seen twice in a row
+	void *last_out = nullptr;
 	float4 *sky = nullptr;
 	int sky_w = 0, sky_h = 0;
 	unsigned int *cursor = nullptr;
@@ -174,7 +176,7 @@ int make_params(srt_tracer *t, const srt_render_data *rd, srt::RenderParams &p) 
 template <bool COUNT, int MODE>
 int launch_render_impl(srt_tracer *t, const srt::RenderParams &p) {
 	auto kernel = srt::render_kernel<COUNT, MODE>;
-	const int smem = MODE == srt::MODE_BIG_MODELS ? srt::RENDER_SMEM_BYTES : srt::QUEUE_SMEM_BYTES;
+	const int smem = MODE == srt::MODE_BIG_MODELS ? srt::RENDER_SMEM_BYTES + srt::BIG_SKYQ_BYTES : srt::QUEUE_SMEM_BYTES;
 	int &grid = t->render_grid[COUNT ? 1 : 0][MODE];
 	if (grid == 0) {
 		int per_sm = 0;
@@ -285,6 +287,8 @@ int srt_destroy(srt_tracer *t) {
 		cudaEventDestroy(e.first);
 		cudaEventDestroy(e.second);
 	}
+	if (t->registered_out) cudaHostUnregister(t->registered_out);
+	cudaGetLastError();
 	cudaFree(t->canvas);
 	cudaFree(t->output);
 	cudaFreeHost(t->pinned_out);
@@ -433,11 +437,26 @@ int srt_resolve(srt_tracer *t, uint32_t num_steps, uint8_t *argb_out) {
 	if (!argb_out) return fail(t, SRT_ERR_INVALID, "output is null");
 	if (int rc = srt_resolve_device(t, num_steps)) return rc;
 	const size_t bytes = (size_t)t->width * t->height * 4;
-	// D2H into the handle's pinned staging buffer, then into the caller's (pageable) vector:
-	// the blocking read of tracer.cpp:115
-	SRT_CUDA(t, cudaMemcpyAsync(t->pinned_out, t->output, bytes, cudaMemcpyDeviceToHost, t->stream));
-	SRT_CUDA(t, cudaStreamSynchronize(t->stream));
-	memcpy(argb_out, t->pinned_out, bytes);
+	// The blocking read of tracer.cpp:115.  The reference's caller hands in the same `pixels` vector every
+	// frame (src/main.cpp:128,290), so it is page-locked the second time it is seen and the copy lands in it directly;
+	// if that is refused (e.g. the memory is already registered) the handle's pinned staging buffer is used.
+	if (t->registered_out != argb_out) {
+		if (t->registered_out) cudaHostUnregister(t->registered_out);
+		t->registered_out = nullptr;
+		if (t->last_out == argb_out) {  // second frame into the same vector: worth page-locking
+			if (cudaHostRegister(argb_out, bytes, cudaHostRegisterDefault) == cudaSuccess) t->registered_out = argb_out;
+			else cudaGetLastError();
+		}
+		t->last_out = argb_out;
+	}
+	if (t->registered_out == argb_out) {
+		SRT_CUDA(t, cudaMemcpyAsync(argb_out, t->output, bytes, cudaMemcpyDeviceToHost, t->stream));
+		SRT_CUDA(t, cudaStreamSynchronize(t->stream));
+	} else {
+		SRT_CUDA(t, cudaMemcpyAsync(t->pinned_out, t->output, bytes, cudaMemcpyDeviceToHost, t->stream));
+		SRT_CUDA(t, cudaStreamSynchronize(t->stream));
+		memcpy(argb_out, t->pinned_out, bytes);
+	}
 	return SRT_OK;
 }
 
