@@ -14,7 +14,8 @@ Keys printed (one JSON line, rank 0): see the driver contract; plus
   roofline      bound = fp32 (the path is FP32-pipe bound: SURVEY 8d / BASELINE.md section 2), achieved =
                 counted algorithmic flop per `render` launch / mean launch duration (CUDA events on the
                 launching stream), peak = FMA-chain micro-benchmark measured in this run
-  cpu_baseline  the oracle port (OpenMP, all host cores) on a bounded sample of the same workload
+  cpu_baseline  the reference kernel itself (oracle/_ref = render.cl compiled by g++, OpenMP, all host cores) on
+                a bounded sample of the same workload
   e2e           the same metric through the reference-facing Tracer API with host buffers: per step
                 update_scene (H2D), clear_canvas, 16 x render(ticks, output) each with its ARGB8 read-back
 """
@@ -84,13 +85,18 @@ class ClockSampler:
 
 
 def cpu_reference_run(scene, sky, steps, warmup, budget_s=4.0):
-    """The reference algorithm on host cores: oracle port, OpenMP over rows, all cores.  A step is a
-    bounded sample of the workload: `n` full-frame launches, n chosen so a step takes about budget_s."""
+    """The reference's CPU path on host cores, all of them.  kind "reference": oracle/_ref, i.e. the
+    reference's own src/render.cl compiled by g++ (built in the authoring container, shipped as a .so) with
+    the NDRange rows spread over OpenMP threads; kind "port" (only if that library is missing): oracle.c.
+    A step is a bounded sample of the workload: `n` full-frame launches, n chosen so a step takes about
+    budget_s."""
     import oracle
     oracle.build()
     cores = oracle.max_threads()
+    impl, kind = ("ref", "reference") if oracle.build_ref() else ("oracle", "port")
     t0 = time.perf_counter()
-    oracle.render(scene.render_data(0), scene.scene_data, scene.shapes, scene.triangles, scene.materials, sky)
+    oracle.render(scene.render_data(0), scene.scene_data, scene.shapes, scene.triangles, scene.materials, sky,
+                  impl=impl)
     t_launch = time.perf_counter() - t0
     n = int(max(1, min(scene.launches, round(budget_s / max(t_launch, 1e-3)))))
     samples_step = scene.width * scene.height * scene.num_samples * n
@@ -100,15 +106,15 @@ def cpu_reference_run(scene, sky, steps, warmup, budget_s=4.0):
         t0 = time.perf_counter()
         for k in range(n):
             canvas, _ = oracle.render(scene.render_data(k), scene.scene_data, scene.shapes, scene.triangles,
-                                      scene.materials, sky, canvas)
-        oracle.average(n, canvas)
+                                      scene.materials, sky, canvas, impl=impl)
+        oracle.average(n, canvas, impl=impl)
         dt = time.perf_counter() - t0
         if s >= warmup:
             times.append(dt)
     total = sum(times)
     value = samples_step * len(times) / total / 1e6
     sample = f"{scene.width}x{scene.height} full frame, {n} of {scene.launches} launches x {scene.num_samples} spp per step"
-    return value, total / len(times) * 1e3, cores, sample
+    return value, total / len(times) * 1e3, cores, sample, kind
 
 
 def main():
@@ -135,15 +141,17 @@ def main():
         if rank != 0:
             return 0
         sky = scenes.procedural_skybox()
-        value, ms, cores, sample = cpu_reference_run(scene, sky, args.steps, args.warmup)
+        value, ms, cores, sample, kind = cpu_reference_run(scene, sky, args.steps, args.warmup)
         print(json.dumps({
             "impl": "reference", "metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload,
-            "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "note": "reference render.cl needs an OpenCL runtime (none in this image); this is oracle/oracle.c, "
-                    "its scalar C restatement, OpenMP over rows on all host cores"}))
+            "note": ("the reference's own src/render.cl compiled for the host by g++ -O2 (oracle/_ref: OpenCL-C shim + "
+                     "NDRange loop, OpenMP over rows, all host cores); no OpenCL runtime exists in this image"
+                     if kind == "reference" else
+                     "oracle/_ref is missing: oracle/oracle.c, the scalar C restatement of render.cl, OpenMP over rows")}))
         return 0
 
     import torch
@@ -277,8 +285,8 @@ def main():
 
     cpu_baseline = None
     if not args.no_cpu_baseline:
-        v, ms, cores, sample = cpu_reference_run(scene, sky, steps=2, warmup=0, budget_s=6.0)
-        cpu_baseline = {"value": v, "unit": "Msamples/s", "cores": cores, "kind": "port", "sample": sample}
+        v, ms, cores, sample, kind = cpu_reference_run(scene, sky, steps=2, warmup=0, budget_s=6.0)
+        cpu_baseline = {"value": v, "unit": "Msamples/s", "cores": cores, "kind": kind, "sample": sample}
 
     print(json.dumps({
         "metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
@@ -287,7 +295,7 @@ def main():
         "config": dict(workload, parallelism=f"sample-sharded x{world}" if world > 1 else "single GPU",
                        l2="flushed between timed steps (256 MiB memset, outside the event pairs)",
                        timing="CUDA events per step on the launching stream, summed; max over ranks"),
-        "clocks": clocks, "gpu_launches": args.steps * (L + 1),
+        "clocks": clocks, "gpu_launches": args.steps * (2 * L + 1),  # per step: L x (render + accumulate) + average
         "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "api": "Tracer.update_scene + clear_canvas + 16 x Tracer.render(ticks, host_output) per step, wall clock"},
         "roofline": roofline, "cpu_baseline": cpu_baseline,

@@ -103,11 +103,11 @@ typedef struct {
 
 static inline v3 f3(cl_f3 a) { return v3_make(a.x, a.y, a.z); }
 
-/* render.cl:114-120 -- row k = fma(m3.k,w, fma(m2.k,z, fma(m1.k,y, m0.k*x))) */
+/* render.cl:114-120 -- row k = ((m0.k*x + m1.k*y) + m2.k*z) + m3.k*w, left to right */
 static inline v3 matrix_by_vector3(const cl_f4 *m, v3 v, float w) {
-	return v3_make(om_fma(m[3].x, w, om_fma(m[2].x, v.z, om_fma(m[1].x, v.y, m[0].x * v.x))),
-	               om_fma(m[3].y, w, om_fma(m[2].y, v.z, om_fma(m[1].y, v.y, m[0].y * v.x))),
-	               om_fma(m[3].z, w, om_fma(m[2].z, v.z, om_fma(m[1].z, v.y, m[0].z * v.x))));
+	return v3_make(om_cfma(m[3].x, w, om_cfma(m[2].x, v.z, om_cfma(m[1].x, v.y, m[0].x * v.x))),
+	               om_cfma(m[3].y, w, om_cfma(m[2].y, v.z, om_cfma(m[1].y, v.y, m[0].y * v.x))),
+	               om_cfma(m[3].z, w, om_cfma(m[2].z, v.z, om_cfma(m[1].z, v.y, m[0].z * v.x))));
 }
 /* render.cl:135-137 */
 static inline v3 transform_mat(const cl_f4 *m, v3 p, int translate) {
@@ -116,8 +116,11 @@ static inline v3 transform_mat(const cl_f4 *m, v3 p, int translate) {
 /* render.cl:139-141:  v - 2*dot(v,n)*n */
 static inline v3 reflect(v3 v, v3 n) {
 	float k = 2.0f * v3_dot(v, n);
-	return v3_make(om_fma(-k, n.x, v.x), om_fma(-k, n.y, v.y), om_fma(-k, n.z, v.z));
+	return v3_make(om_cfma(-k, n.x, v.x), om_cfma(-k, n.y, v.y), om_cfma(-k, n.z, v.z));
 }
+
+/* render.cl:165-167: written out by the source as x*x + y*y + z*z, not a dot() call */
+static inline float length_squared(v3 v) { return om_cfma(v.z, v.z, om_cfma(v.y, v.y, v.x * v.x)); }
 
 /* render.cl:143-148.  (float)UINT_MAX == 2^32, so the division is an exact scaling. */
 static inline uint32_t rng_hash(uint32_t *seed) {
@@ -160,8 +163,8 @@ static inline float shlick_reflectance(float mu, float cos_theta) {
 static inline int intersect_sphere(const Sphere *sphere, const Ray *ray, float *t) {
 	v3 rayToCenter = v3_sub(f3(sphere->position), ray->origin);
 	float b = v3_dot(rayToCenter, ray->direction);
-	float c = om_fma(-sphere->radius, sphere->radius, v3_dot(rayToCenter, rayToCenter));
-	float disc = om_fma(b, b, -c);
+	float c = om_cfma(-sphere->radius, sphere->radius, v3_dot(rayToCenter, rayToCenter));
+	float disc = om_cfma(b, b, -c);
 	if (disc < 0.0f) return 0;
 	float sq = om_sqrt(disc);
 	*t = b - sq;
@@ -191,9 +194,9 @@ static inline v3 barycentric_weights(const v3 pos[3], v3 p) {
 	float d11 = v3_dot(v1, v1);
 	float d20 = v3_dot(v2, v0);
 	float d21 = v3_dot(v2, v1);
-	float denom = om_fma(d00, d11, -(d01 * d01));
-	float w0 = om_fma(d11, d20, -(d01 * d21)) / denom;
-	float w1 = om_fma(d00, d21, -(d01 * d20)) / denom;
+	float denom = om_cfma(d00, d11, -(d01 * d01));
+	float w0 = om_cfma(d11, d20, -(d01 * d21)) / denom;
+	float w1 = om_cfma(d00, d21, -(d01 * d20)) / denom;
 	float w2 = (1.0f - w0) - w1;
 	return v3_make(w2, w0, w1);
 }
@@ -247,7 +250,7 @@ static int closest_intersection(const Scene *scene, const Ray *ray, Intersection
 				tmin = t_i;
 				closest = shape->material;
 				closest_shape = i;
-				rayhit->position = v3_fma(ray->direction, tmin, ray->origin);
+				rayhit->position = v3_cfma(ray->direction, tmin, ray->origin);
 				float r = sphere->radius;
 				v3 d = v3_sub(rayhit->position, f3(sphere->position));
 				rayhit->normal = v3_make(d.x / r, d.y / r, d.z / r);
@@ -267,13 +270,13 @@ static int closest_intersection(const Scene *scene, const Ray *ray, Intersection
 					tmin = t_i;
 					closest = shape->material;
 					closest_shape = i;
-					rayhit->position = v3_fma(ray->direction, tmin, ray->origin);
+					rayhit->position = v3_cfma(ray->direction, tmin, ray->origin);
 					v3 w = barycentric_weights(pos, rayhit->position);
 					v3 n0 = f3(tri->v[0].normal), n1 = f3(tri->v[1].normal), n2 = f3(tri->v[2].normal);
 					/* n0*w.x + n1*w.y + n2*w.z */
-					v3 n = v3_make(om_fma(n2.x, w.z, om_fma(n1.x, w.y, n0.x * w.x)),
-					               om_fma(n2.y, w.z, om_fma(n1.y, w.y, n0.y * w.x)),
-					               om_fma(n2.z, w.z, om_fma(n1.z, w.y, n0.z * w.x)));
+					v3 n = v3_make(om_cfma(n2.x, w.z, om_cfma(n1.x, w.y, n0.x * w.x)),
+					               om_cfma(n2.y, w.z, om_cfma(n1.y, w.y, n0.y * w.x)),
+					               om_cfma(n2.z, w.z, om_cfma(n1.z, w.y, n0.z * w.x)));
 					n = transform_mat(model->transform, n, 0);
 					rayhit->normal = v3_normalize(n);
 				}
@@ -286,7 +289,7 @@ static int closest_intersection(const Scene *scene, const Ray *ray, Intersection
 				closest = shape->material;
 				closest_shape = i;
 				rayhit->normal = f3(plane->normal);
-				rayhit->position = v3_fma(ray->direction, tmin, ray->origin);
+				rayhit->position = v3_cfma(ray->direction, tmin, ray->origin);
 			}
 		}
 	}
@@ -300,27 +303,10 @@ static int closest_intersection(const Scene *scene, const Ray *ray, Intersection
 	return closest;
 }
 
-/* read_imagef with CLK_NORMALIZED_COORDS_TRUE | CLAMP_TO_EDGE | FILTER_LINEAR on an RGBA float
- * image (src/tracer.cpp:47-48), OpenCL 2.0 spec 8.2: u' = u*w, i0 = floor(u'-0.5), a = frac. */
+/* read_imagef(...).xyz, render.cl:393: the builtin is defined in oracle_math.h */
 static inline v3 sky_fetch(const Scene *scene, float u, float v) {
-	int w = scene->sky_w, h = scene->sky_h;
-	float fu = om_fma(u, (float)w, -0.5f), fv = om_fma(v, (float)h, -0.5f);
-	float flu = __builtin_floorf(fu), flv = __builtin_floorf(fv);
-	float a = fu - flu, b = fv - flv;
-	int i0 = (int)flu, j0 = (int)flv;
-	int i1 = i0 + 1, j1 = j0 + 1;
-	if (i0 < 0) i0 = 0; if (i0 > w - 1) i0 = w - 1;
-	if (i1 < 0) i1 = 0; if (i1 > w - 1) i1 = w - 1;
-	if (j0 < 0) j0 = 0; if (j0 > h - 1) j0 = h - 1;
-	if (j1 < 0) j1 = 0; if (j1 > h - 1) j1 = h - 1;
-	const float *t00 = scene->sky + 4 * ((size_t)j0 * w + i0);
-	const float *t10 = scene->sky + 4 * ((size_t)j0 * w + i1);
-	const float *t01 = scene->sky + 4 * ((size_t)j1 * w + i0);
-	const float *t11 = scene->sky + 4 * ((size_t)j1 * w + i1);
-	float w00 = (1.0f - a) * (1.0f - b), w10 = a * (1.0f - b), w01 = (1.0f - a) * b, w11 = a * b;
-	float r[3];
-	for (int c = 0; c < 3; c++)
-		r[c] = om_fma(w11, t11[c], om_fma(w01, t01[c], om_fma(w10, t10[c], w00 * t00[c])));
+	float r[4];
+	om_read_imagef_linear_clamp(scene->sky, scene->sky_w, scene->sky_h, u, v, r);
 	return v3_make(r[0], r[1], r[2]);
 }
 /* render.cl:380-394 */
@@ -329,8 +315,8 @@ static v3 sky_box(const Ray *ray, const Scene *scene) {
 	float sd = om_max(v3_dot(ray->direction, v3_neg(f3(d->sun_direction))), 0.0f);
 	float pw = om_pow(sd, d->sun_focus);
 	v3 sun = v3_scale(v3_scale(f3(d->sun_color), pw), d->sun_intensity);
-	float u = om_fma(om_atan2pi(ray->direction.z, ray->direction.x), 0.5f, 0.5f);
-	float v = om_fma(ray->direction.y, 0.5f, 0.5f);
+	float u = om_cfma(om_atan2pi(ray->direction.z, ray->direction.x), 0.5f, 0.5f);
+	float v = om_cfma(ray->direction.y, 0.5f, 0.5f);
 	return v3_add(sky_fetch(scene, u, v), sun);
 }
 
@@ -348,8 +334,8 @@ static v3 trace(const RenderData *render, const Scene *scene, const Ray *camray,
 		if (material_index >= 0) {
 			cnt->hits++;
 			if (render->show_normals) {
-				color = v3_make(om_fma(rayhit.normal.x, 0.5f, 0.5f), om_fma(rayhit.normal.y, 0.5f, 0.5f),
-				                om_fma(rayhit.normal.z, 0.5f, 0.5f));
+				color = v3_make(om_cfma(rayhit.normal.x, 0.5f, 0.5f), om_cfma(rayhit.normal.y, 0.5f, 0.5f),
+				                om_cfma(rayhit.normal.z, 0.5f, 0.5f));
 				break;
 			}
 			const Material *material = &scene->materials[material_index];
@@ -375,22 +361,22 @@ static v3 trace(const RenderData *render, const Scene *scene, const Ray *camray,
 				v3 in_dir = reflect(rough_dir, rayhit.normal);
 				float mu = rayhit.front ? 1.0f / material->refraction_index : material->refraction_index;
 				float cos_theta = om_min(1.0f, v3_dot(in_dir, v3_neg(rayhit.normal)));
-				float sin_theta = om_sqrt(om_fma(-cos_theta, cos_theta, 1.0f));
+				float sin_theta = om_sqrt(om_cfma(-cos_theta, cos_theta, 1.0f));
 				int transparency_reflected = mu * sin_theta > 1.0f ||
 				                             shlick_reflectance(mu, cos_theta) > random_float(&seed);
 				if (transparency_reflected) {
 					ray.direction = rough_dir;
 				} else {
-					v3 out_perp = v3_scale(v3_fma(rayhit.normal, cos_theta, in_dir), mu);
-					float k = -om_sqrt(__builtin_fabsf(1.0f - v3_dot(out_perp, out_perp)));
-					ray.direction = v3_fma(rayhit.normal, k, out_perp);
+					v3 out_perp = v3_scale(v3_cfma(rayhit.normal, cos_theta, in_dir), mu);
+					float k = -om_sqrt(__builtin_fabsf(1.0f - length_squared(out_perp)));
+					ray.direction = v3_cfma(rayhit.normal, k, out_perp);
 					mask = v3_mul(mask, f3(material->color));
 				}
 			}
 			ray.direction = v3_normalize(ray.direction);
 			/* origin += normal * sign(dot(normal, dir)) * 0.001 */
 			float sg = om_sign(v3_dot(rayhit.normal, ray.direction)) * 0.001f;
-			ray.origin = v3_fma(rayhit.normal, sg, ray.origin);
+			ray.origin = v3_cfma(rayhit.normal, sg, ray.origin);
 		} else {
 			cnt->sky++;
 			mask = v3_mul(mask, sky_box(&ray, scene));
@@ -411,8 +397,8 @@ static inline Ray camera_ray(const RenderData *data, int gx, int gy, uint32_t *s
 	float u1 = random_float(seed);
 	float ndc_x = ((float)gx + u0) / (float)data->width;
 	float ndc_y = ((float)gy + u1) / (float)data->height;
-	float sx = (om_fma(2.0f, ndc_x, -1.0f) * data->aspect_ratio) * data->fov_scale;
-	float sy = om_fma(-2.0f, ndc_y, 1.0f) * data->fov_scale;
+	float sx = (om_cfma(2.0f, ndc_x, -1.0f) * data->aspect_ratio) * data->fov_scale;
+	float sy = om_cfma(-2.0f, ndc_y, 1.0f) * data->fov_scale;
 	Ray ray;
 	ray.origin = v3_make(data->camera_to_world[3].x, data->camera_to_world[3].y, data->camera_to_world[3].z);
 	ray.direction = v3_normalize(matrix_by_vector3(data->camera_to_world, v3_make(sx, sy, -1.0f), 0.0f));
@@ -504,13 +490,9 @@ void oracle_primary(const RenderData *data, const SceneData *scene_data, const S
 /* render.cl:473-481 */
 static inline float aces1(float x) {
 	const float a = 2.51f, b = 0.03f, c = 2.43f, d = 0.59f, e = 0.14f;
-	float num = x * om_fma(x, a, b);
-	float den = om_fma(x, om_fma(x, c, d), e);
-	float r = num / den;
-	/* clamp(x,0,1) = min(max(x,0),1); NaN -> 0 by the comparison form (hazard ix) */
-	r = r > 0.0f ? r : 0.0f;
-	r = r < 1.0f ? r : 1.0f;
-	return r;
+	float num = x * om_cfma(x, a, b);
+	float den = om_cfma(x, om_cfma(x, c, d), e);
+	return om_clamp(num / den, 0.0f, 1.0f); /* NaN -> 0 (hazard ix) */
 }
 /* kernel `average`, render.cl:525-535: canvas/num_steps -> aces -> sqrt -> ARGB8 (truncating) */
 void oracle_average(uint32_t num_steps, const float *canvas, uint8_t *output, size_t n) {

@@ -32,6 +32,25 @@ static inline uint64_t om_d2u(double f) { uint64_t u; memcpy(&u, &f, 8); return 
 static inline double om_u2d(uint64_t u) { double f; memcpy(&f, &u, 8); return f; }
 
 static inline float om_fma(float a, float b, float c) { return __builtin_fmaf(a, b, c); }
+/* a*b + c where render.cl itself writes a multiply feeding an add or subtract in one expression
+ * (e.g. `b * b - c`, :188; `origin + direction * tmin`, :311), as opposed to arithmetic INSIDE a builtin.
+ * OpenCL C leaves such a pair to the compiler (FP_CONTRACT defaults to ON).  The contract of this
+ * repository is the conforming baseline every compiler can produce and the one that can be checked
+ * against the reference source itself (oracle/_ref: render.cl compiled by g++ -ffp-contract=off): the
+ * product and the sum are rounded separately.  -DORACLE_CONTRACT=1 builds the variant in which every such
+ * site is fused instead; tests/test_ref_parity.py uses it to measure how far a contracting compiler
+ * could move the image (the tolerances of SURVEY 8c). */
+#ifndef ORACLE_CONTRACT
+#define ORACLE_CONTRACT 0
+#endif
+static inline float om_cfma(float a, float b, float c) {
+#if ORACLE_CONTRACT
+	return __builtin_fmaf(a, b, c);
+#else
+	float p = a * b;
+	return p + c;
+#endif
+}
 static inline float om_sqrt(float a) { return __builtin_sqrtf(a); }
 
 /* OpenCL fmin/fmax on NaN are left open by the slab test (render.cl:285-286); we pin them as
@@ -49,6 +68,11 @@ static inline float om_sign(float x) {
 
 /* mix(x,y,a) = x + (y-x)*a, fused (render.cl:427,:432,:436). */
 static inline float om_mix(float x, float y, float a) { return om_fma(y - x, a, x); }
+/* clamp(x,lo,hi) = fmin(fmax(x,lo),hi) (render.cl:480); fmax returns the non-NaN operand, so NaN -> lo. */
+static inline float om_clamp(float x, float lo, float hi) {
+	x = x > lo ? x : lo;
+	return x < hi ? x : hi;
+}
 
 static inline v3 v3_make(float x, float y, float z) { v3 r = {x, y, z}; return r; }
 static inline v3 v3_add(v3 a, v3 b) { return v3_make(a.x + b.x, a.y + b.y, a.z + b.z); }
@@ -56,9 +80,9 @@ static inline v3 v3_sub(v3 a, v3 b) { return v3_make(a.x - b.x, a.y - b.y, a.z -
 static inline v3 v3_mul(v3 a, v3 b) { return v3_make(a.x * b.x, a.y * b.y, a.z * b.z); }
 static inline v3 v3_scale(v3 a, float s) { return v3_make(a.x * s, a.y * s, a.z * s); }
 static inline v3 v3_neg(v3 a) { return v3_make(-a.x, -a.y, -a.z); }
-/* a*s + b, fused per component */
-static inline v3 v3_fma(v3 a, float s, v3 b) {
-	return v3_make(om_fma(a.x, s, b.x), om_fma(a.y, s, b.y), om_fma(a.z, s, b.z));
+/* a*s + b per component at a render.cl expression site (see om_cfma) */
+static inline v3 v3_cfma(v3 a, float s, v3 b) {
+	return v3_make(om_cfma(a.x, s, b.x), om_cfma(a.y, s, b.y), om_cfma(a.z, s, b.z));
 }
 /* dot = fma(z,z', fma(y,y', x*x')) */
 static inline float v3_dot(v3 a, v3 b) { return om_fma(a.z, b.z, om_fma(a.y, b.y, a.x * b.x)); }
@@ -209,6 +233,28 @@ static inline float om_pow(float x, float y) {
 	if (z < -104.0) return 0.0f;
 	if (z > 89.0) return INFINITY;
 	return (float)om_exp_d(z);
+}
+
+/* read_imagef(image, CLK_NORMALIZED_COORDS_TRUE | CLK_ADDRESS_CLAMP_TO_EDGE | CLK_FILTER_LINEAR, (u,v)) on a
+ * CL_RGBA / CL_FLOAT image (src/tracer.cpp:42-52, render.cl:393), OpenCL 2.0 spec 8.2: u' = u*w,
+ * i0 = floor(u' - 0.5), a = frac(u' - 0.5), indices clamped to the edge, weights (1-a)(1-b) ... in FP32. */
+static inline void om_read_imagef_linear_clamp(const float *texels, int w, int h, float u, float v, float out[4]) {
+	float fu = om_fma(u, (float)w, -0.5f), fv = om_fma(v, (float)h, -0.5f);
+	float flu = __builtin_floorf(fu), flv = __builtin_floorf(fv);
+	float a = fu - flu, b = fv - flv;
+	int i0 = (int)flu, j0 = (int)flv;
+	int i1 = i0 + 1, j1 = j0 + 1;
+	if (i0 < 0) i0 = 0; if (i0 > w - 1) i0 = w - 1;
+	if (i1 < 0) i1 = 0; if (i1 > w - 1) i1 = w - 1;
+	if (j0 < 0) j0 = 0; if (j0 > h - 1) j0 = h - 1;
+	if (j1 < 0) j1 = 0; if (j1 > h - 1) j1 = h - 1;
+	const float *t00 = texels + 4 * ((size_t)j0 * w + i0);
+	const float *t10 = texels + 4 * ((size_t)j0 * w + i1);
+	const float *t01 = texels + 4 * ((size_t)j1 * w + i0);
+	const float *t11 = texels + 4 * ((size_t)j1 * w + i1);
+	float w00 = (1.0f - a) * (1.0f - b), w10 = a * (1.0f - b), w01 = (1.0f - a) * b, w11 = a * b;
+	for (int c = 0; c < 4; c++)
+		out[c] = om_fma(w11, t11[c], om_fma(w01, t01[c], om_fma(w10, t10[c], w00 * t00[c])));
 }
 
 #endif

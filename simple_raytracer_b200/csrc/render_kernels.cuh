@@ -129,8 +129,8 @@ __device__ __forceinline__ int scan_shapes(const DevScene &sc, vec3 o, vec3 d, v
 			// intersect_sphere, :180-204
 			vec3 L = xyz(a) - o;
 			float b = dot(L, d);
-			float c = fma_(-a.w, a.w, dot(L, L));
-			float disc = fma_(b, b, -c);
+			float c = cfma_(-a.w, a.w, dot(L, L));
+			float disc = cfma_(b, b, -c);
 			if (disc >= 0.0f) {
 				float sq = sqrt_(disc);
 				float t = b - sq;
@@ -190,7 +190,7 @@ __device__ __forceinline__ void finish_hit(const DevScene &sc, const Hit &hit, v
 	const int4 hdr = __ldg(&sc.shape_hdr[hit.shape]);
 	const float4 a = __ldg(&sc.shape_a[hit.shape]);
 	material = hdr.y;
-	pos = fma3(d, hit.t, o);
+	pos = cfma3(d, hit.t, o);
 	if (hdr.x == SHAPE_SPHERE) {
 		vec3 r = pos - xyz(a);
 		n = mk(div_(r.x, a.w), div_(r.y, a.w), div_(r.z, a.w));
@@ -204,24 +204,24 @@ __device__ __forceinline__ void finish_hit(const DevScene &sc, const Hit &hit, v
 		vec3 v2 = pos - v0;
 		float d00 = dot(e1, e1), d01 = dot(e1, e2), d11 = dot(e2, e2);
 		float d20 = dot(v2, e1), d21 = dot(v2, e2);
-		float denom = fma_(d00, d11, -(d01 * d01));
-		float w0 = div_(fma_(d11, d20, -(d01 * d21)), denom);
-		float w1 = div_(fma_(d00, d21, -(d01 * d20)), denom);
+		float denom = cfma_(d00, d11, -(d01 * d01));
+		float w0 = div_(cfma_(d11, d20, -(d01 * d21)), denom);
+		float w1 = div_(cfma_(d00, d21, -(d01 * d20)), denom);
 		float w2 = (1.0f - w0) - w1;
 		vec3 n0 = xyz(__ldg(&sc.tri_n[3 * hit.tri + 0]));
 		vec3 n1 = xyz(__ldg(&sc.tri_n[3 * hit.tri + 1]));
 		vec3 n2 = xyz(__ldg(&sc.tri_n[3 * hit.tri + 2]));
 		// n0*w2 + n1*w0 + n2*w1  (:341 with the rotated weights)
-		vec3 ns = mk(fma_(n2.x, w1, fma_(n1.x, w0, n0.x * w2)), fma_(n2.y, w1, fma_(n1.y, w0, n0.y * w2)),
-		             fma_(n2.z, w1, fma_(n1.z, w0, n0.z * w2)));
+		vec3 ns = mk(cfma_(n2.x, w1, cfma_(n1.x, w0, n0.x * w2)), cfma_(n2.y, w1, cfma_(n1.y, w0, n0.y * w2)),
+		             cfma_(n2.z, w1, cfma_(n1.z, w0, n0.z * w2)));
 		// transform_mat(model->transform, n, false), :342 (model matrix, w = 0)
 		const float4 m0 = __ldg(&sc.model_xf[4 * hit.shape + 0]);
 		const float4 m1 = __ldg(&sc.model_xf[4 * hit.shape + 1]);
 		const float4 m2 = __ldg(&sc.model_xf[4 * hit.shape + 2]);
 		const float4 m3 = __ldg(&sc.model_xf[4 * hit.shape + 3]);
-		vec3 nt = mk(fma_(m3.x, 0.0f, fma_(m2.x, ns.z, fma_(m1.x, ns.y, m0.x * ns.x))),
-		             fma_(m3.y, 0.0f, fma_(m2.y, ns.z, fma_(m1.y, ns.y, m0.y * ns.x))),
-		             fma_(m3.z, 0.0f, fma_(m2.z, ns.z, fma_(m1.z, ns.y, m0.z * ns.x))));
+		vec3 nt = mk(cfma_(m3.x, 0.0f, cfma_(m2.x, ns.z, cfma_(m1.x, ns.y, m0.x * ns.x))),
+		             cfma_(m3.y, 0.0f, cfma_(m2.y, ns.z, cfma_(m1.y, ns.y, m0.y * ns.x))),
+		             cfma_(m3.z, 0.0f, cfma_(m2.z, ns.z, cfma_(m1.z, ns.y, m0.z * ns.x))));
 		n = normalize(nt);
 	}
 	front = dot(n, d) < 0.0f;
@@ -235,8 +235,9 @@ __device__ __forceinline__ vec3 sky_box(const DevScene &sc, vec3 d) {
 	float sd = max_(dot(d, -sun_dir), 0.0f);
 	float pw = pow_(sd, sc.sun_focus);
 	vec3 sun = (mk(sc.sun_color[0], sc.sun_color[1], sc.sun_color[2]) * pw) * sc.sun_intensity;
-	float u = fma_(atan2pi_(d.z, d.x), 0.5f, 0.5f);
-	float v = fma_(d.y, 0.5f, 0.5f);
+	float u = cfma_(atan2pi_(d.z, d.x), 0.5f, 0.5f);
+	float v = cfma_(d.y, 0.5f, 0.5f);
+	// read_imagef: the arithmetic inside the builtin stays fused
 	const int w = sc.sky_w, h = sc.sky_h;
 	float fu = fma_(u, (float)w, -0.5f), fv = fma_(v, (float)h, -0.5f);
 	float flu = floorf(fu), flv = floorf(fv);
@@ -265,14 +266,14 @@ __device__ __forceinline__ void camera_ray(const RenderParams &p, int gx, int gy
 	float u1 = random_float(seed);
 	float ndc_x = div_((float)gx + u0, (float)p.width);
 	float ndc_y = div_((float)gy + u1, (float)p.height);
-	float sx = (fma_(2.0f, ndc_x, -1.0f) * p.aspect_ratio) * p.fov_scale;
-	float sy = fma_(-2.0f, ndc_y, 1.0f) * p.fov_scale;
+	float sx = (cfma_(2.0f, ndc_x, -1.0f) * p.aspect_ratio) * p.fov_scale;
+	float sy = cfma_(-2.0f, ndc_y, 1.0f) * p.fov_scale;
 	const float *m = p.c2w;
 	o = mk(m[12], m[13], m[14]);
 	// matrix_by_vector(camera_to_world, (sx, sy, -1, 0)), :114-120
-	vec3 t = mk(fma_(m[12], 0.0f, fma_(m[8], -1.0f, fma_(m[4], sy, m[0] * sx))),
-	            fma_(m[13], 0.0f, fma_(m[9], -1.0f, fma_(m[5], sy, m[1] * sx))),
-	            fma_(m[14], 0.0f, fma_(m[10], -1.0f, fma_(m[6], sy, m[2] * sx))));
+	vec3 t = mk(cfma_(m[12], 0.0f, cfma_(m[8], -1.0f, cfma_(m[4], sy, m[0] * sx))),
+	            cfma_(m[13], 0.0f, cfma_(m[9], -1.0f, cfma_(m[5], sy, m[1] * sx))),
+	            cfma_(m[14], 0.0f, cfma_(m[10], -1.0f, cfma_(m[6], sy, m[2] * sx))));
 	d = normalize(t);
 }
 
@@ -288,7 +289,7 @@ __device__ __forceinline__ void scatter(const DevScene &sc, int material, vec3 p
 	rd = rd * sign_(dot(n, rd));
 	vec3 random_dir = normalize(n + rd);                       // :421
 	float k2 = 2.0f * dot(d, n);                                // reflect, :139-141
-	vec3 reflected = mk(fma_(-k2, n.x, d.x), fma_(-k2, n.y, d.y), fma_(-k2, n.z, d.z));
+	vec3 reflected = mk(cfma_(-k2, n.x, d.x), cfma_(-k2, n.y, d.y), cfma_(-k2, n.z, d.z));
 	const bool is_metallic = m0.y > random_float(seed);         // :424
 	const bool is_specular = m0.z > random_float(seed);         // :425
 	vec3 rough = mix3(random_dir, reflected, m0.x);             // :427
@@ -301,24 +302,24 @@ __device__ __forceinline__ void scatter(const DevScene &sc, int material, vec3 p
 		mask = mask * mk(mix_(col.x, 1.0f, sp), mix_(col.y, 1.0f, sp), mix_(col.z, 1.0f, sp));  // :436
 	} else {
 		float ki = 2.0f * dot(rough, n);                        // in_dir = reflect(rough, n), :440
-		vec3 in_dir = mk(fma_(-ki, n.x, rough.x), fma_(-ki, n.y, rough.y), fma_(-ki, n.z, rough.z));
+		vec3 in_dir = mk(cfma_(-ki, n.x, rough.x), cfma_(-ki, n.y, rough.y), cfma_(-ki, n.z, rough.z));
 		float mu = front ? div_(1.0f, m1.y) : m1.y;             // :442
 		float cos_theta = min_(1.0f, dot(in_dir, -n));          // :443
-		float sin_theta = sqrt_(fma_(-cos_theta, cos_theta, 1.0f));
+		float sin_theta = sqrt_(cfma_(-cos_theta, cos_theta, 1.0f));
 		bool reflected_t = mu * sin_theta > 1.0f;               // :446
 		if (!reflected_t) reflected_t = schlick_(mu, cos_theta) > random_float(seed);  // :447 (short-circuit)
 		if (reflected_t) {
 			nd = rough;                                         // :450
 		} else {
-			vec3 out_perp = fma3(n, cos_theta, in_dir) * mu;    // :452
-			float kp = -sqrt_(fabsf(1.0f - dot(out_perp, out_perp)));  // :453
-			nd = fma3(n, kp, out_perp);                         // :454
+			vec3 out_perp = cfma3(n, cos_theta, in_dir) * mu;   // :452
+			float kp = -sqrt_(fabsf(1.0f - length_squared(out_perp)));  // :453
+			nd = cfma3(n, kp, out_perp);                        // :454
 			mask = mask * xyz(__ldg(&sc.materials[4 * material + 2]));  // :457
 		}
 	}
 	d = normalize(nd);                                          // :461
 	float sg = sign_(dot(n, d)) * 0.001f;                       // :462
-	o = fma3(n, sg, o);
+	o = cfma3(n, sg, o);
 }
 
 // ---- kernel `render` ---------------------------------------------------------------------------
@@ -665,7 +666,7 @@ render_kernel(const __grid_constant__ RenderParams p, const __grid_constant__ De
 					int material;
 					finish_hit(sc, hit, o, d, pos, n, front, material);
 					if (p.show_normals) {  // :407-410
-						color = mk(fma_(n.x, 0.5f, 0.5f), fma_(n.y, 0.5f, 0.5f), fma_(n.z, 0.5f, 0.5f));
+						color = mk(cfma_(n.x, 0.5f, 0.5f), cfma_(n.y, 0.5f, 0.5f), cfma_(n.z, 0.5f, 0.5f));
 						done = true;
 					} else {
 						const float4 m0 = __ldg(&sc.materials[4 * material + 0]);
@@ -779,8 +780,8 @@ accumulate_kernel(const __grid_constant__ RenderParams p, const float4 *__restri
 // ---- kernel `average`, render.cl:525-535 (aces :473-481) ---------------------------------------
 __device__ __forceinline__ float aces_sqrt(float x) {
 	const float a = 2.51f, b = 0.03f, c = 2.43f, dd = 0.59f, e = 0.14f;
-	float num = x * fma_(x, a, b);
-	float den = fma_(x, fma_(x, c, dd), e);
+	float num = x * cfma_(x, a, b);
+	float den = cfma_(x, cfma_(x, c, dd), e);
 	float r = div_(num, den);
 	r = r > 0.0f ? r : 0.0f;  // clamp; NaN -> 0
 	r = r < 1.0f ? r : 1.0f;
@@ -846,9 +847,9 @@ prepare_triangles_kernel(const float4 *__restrict__ aos /* 6 float4 per triangle
 	vec3 w[3];
 	for (int j = 0; j < 3; ++j) {
 		const float4 pj = tri[2 * j + 1];
-		w[j] = mk(fma_(m3.x, 1.0f, fma_(m2.x, pj.z, fma_(m1.x, pj.y, m0.x * pj.x))),
-		          fma_(m3.y, 1.0f, fma_(m2.y, pj.z, fma_(m1.y, pj.y, m0.y * pj.x))),
-		          fma_(m3.z, 1.0f, fma_(m2.z, pj.z, fma_(m1.z, pj.y, m0.z * pj.x))));
+		w[j] = mk(cfma_(m3.x, 1.0f, cfma_(m2.x, pj.z, cfma_(m1.x, pj.y, m0.x * pj.x))),
+		          cfma_(m3.y, 1.0f, cfma_(m2.y, pj.z, cfma_(m1.y, pj.y, m0.y * pj.x))),
+		          cfma_(m3.z, 1.0f, cfma_(m2.z, pj.z, cfma_(m1.z, pj.y, m0.z * pj.x))));
 		n_out[3 * (size_t)g + j] = tri[2 * j];
 	}
 	vec3 e1 = w[1] - w[0], e2 = w[2] - w[0];

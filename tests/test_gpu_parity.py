@@ -1,4 +1,5 @@
-"""Parity of the CUDA path (through the C ABI) with the CPU oracle on the same seeded inputs.
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle and with the reference kernel itself
+(oracle/_ref = render.cl compiled by g++) on the same seeded inputs.
 
 Gate: primary-hit shape ids bit-exact, primary t bit-exact, 1-spp radiance within 1e-4
 relative on >= 99 % of pixels, resolved images within 1 LSB.  Because both sides are built from the
@@ -9,7 +10,7 @@ import pytest
 
 from conftest import assert_bit_equal
 from simple_raytracer_b200 import scenes
-from util import cuda_canvas, make_tracer, oracle_canvas
+from util import cuda_canvas, make_tracer, oracle_canvas, random_scene, ref_primary_ids
 
 pytestmark = pytest.mark.gpu
 
@@ -49,6 +50,43 @@ def test_canvas_bit_exact_and_counters(ctx, cfg, w, h, ns, launches):
     assert rel.all(axis=-1).mean() >= 0.99
     # resolve (kernel `average`): ARGB8 identical
     assert np.array_equal(ctx["oracle"].average(launches, oc), tr.resolve(launches))
+
+
+needs_ref = pytest.mark.skipif(not __import__("oracle").ref_available(), reason="oracle/_ref library not present")
+
+
+@needs_ref
+@pytest.mark.parametrize("cfg,w,h,ns,launches", CASES)
+def test_canvas_bit_exact_against_the_reference_kernel(ctx, cfg, w, h, ns, launches):
+    """The CUDA path against /root/reference/src/render.cl itself (oracle/_ref, built by g++): canvases and
+    resolved images bit-identical, primary-hit shape ids identical on every pixel."""
+    oracle = ctx["oracle"]
+    sc = scenes.CONFIGS[cfg](w, h)
+    tr = make_tracer(sc, ctx["sky"])
+    got = cuda_canvas(tr, sc, launches, num_samples=ns)
+    ref = None
+    for k in range(launches):
+        ref, _ = oracle.render(sc.render_data(k, num_samples=ns), sc.scene_data, sc.shapes, sc.triangles,
+                               sc.materials, ctx["sky"], ref, impl="ref")
+    assert_bit_equal(ref, got, f"C{cfg} canvas vs render.cl")
+    assert np.array_equal(oracle.average(launches, ref, impl="ref"), tr.resolve(launches))
+    rd1 = sc.render_data(0, num_samples=1)
+    gi, _ = tr.debug_primary(rd1)
+    assert np.array_equal(ref_primary_ids(oracle, sc, rd1), gi)
+
+
+@needs_ref
+@pytest.mark.parametrize("seed", range(6))
+def test_random_scenes_against_the_reference_kernel(ctx, seed):
+    oracle = ctx["oracle"]
+    sc = random_scene(seed, width=160, height=96, mesh_tris=(0, 20, 200)[seed % 3])
+    tr = make_tracer(sc, ctx["sky"])
+    for kw in (dict(num_samples=3), dict(num_samples=1, num_bounces=1), dict(num_samples=1, show_normals=True)):
+        rd = sc.render_data(seed, **kw)
+        tr.clear_canvas()
+        tr.accumulate(rd)
+        ref, _ = oracle.render(rd, sc.scene_data, sc.shapes, sc.triangles, sc.materials, ctx["sky"], impl="ref")
+        assert_bit_equal(ref, tr.read_canvas(), f"seed {seed} {kw}")
 
 
 @pytest.mark.parametrize("cfg", [1, 3])
@@ -98,7 +136,7 @@ def test_golden_fixture(cfg):
     tr = Tracer(int(rd["width"][0]), int(rd["height"][0]), g["sky"])
     tr.scene_data[:] = g["scene_data"]
     tr.update_scene(g["shapes"], g["triangles"], g["materials"])
-    idx, t = tr.debug_primary(rd[0:1])
+    idx, t = tr.debug_primary(g["primary_rd"])
     assert np.array_equal(idx, g["primary_idx"])
     assert_bit_equal(t, g["primary_t"], "golden primary t")
     tr.clear_canvas()
