@@ -9,18 +9,20 @@
  * The OpenCL builtins are third-party arithmetic that is NOT under /root/reference: they are
  * supplied by whichever OpenCL driver JIT-compiles render.cl ("default device",
  * src/tracer.cpp:13; no driver or version is pinned by the reference, and no OpenCL runtime
- * exists in this image).  PARITY UNPINNED at this boundary: the definitions below are this
- * repository's documented choices.  Every function is built only from IEEE-754 correctly
- * rounded operations (+ - * / sqrt fma, int<->float conversions), so a CPU compiled with
- * -ffp-contract=off and a GPU compiled with --fmad=false produce the same bits.
- * Polynomials are the published Cephes single-precision kernels (S. Moshier, cephes/single:
- * logf.c, sinf.c, atanf.c).  Every fused multiply-add is spelled fmaf()/fma() explicitly;
- * nothing else may be contracted.
+ * exists in this image).  PARITY UNPINNED at this boundary only: the definitions below are this
+ * repository's documented choices, used by oracle.c AND by the build of the reference kernel itself
+ * (oracle/ref_build/cl_shim.hpp forwards every builtin here), so the two can be compared bit for bit.
+ * Every function is built only from IEEE-754 correctly rounded operations (+ - * / sqrt fma,
+ * int<->float conversions), so a CPU compiled with -ffp-contract=off and a GPU compiled with
+ * --fmad=false produce the same bits.  Polynomials are the published Cephes single-precision kernels
+ * (S. Moshier, cephes/single: logf.c, sinf.c, atanf.c).  Fused multiply-adds occur only INSIDE these
+ * builtins, spelled fmaf()/fma() explicitly; render.cl's own expressions are not contracted (om_cfma).
  */
 #ifndef ORACLE_MATH_H
 #define ORACLE_MATH_H
 
 #include <math.h>
+#include <stddef.h>
 #include <stdint.h>
 #include <string.h>
 
