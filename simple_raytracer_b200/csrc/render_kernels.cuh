@@ -28,6 +28,7 @@ struct DevScene {
 	const float4 *shape_a;    // sphere {c.xyz, r} | plane {p0.xyz, -} | model {bmin.xyz, -}
 	const float4 *shape_b;    // sphere {-}        | plane {n.xyz, -}  | model {bmax.xyz, -}
 	const float4 *tri_hot;    // 3 per triangle, 48 B stride: world-space v0, e1 = v1-v0, e2 = v2-v0 (+1 pad triangle)
+	const float4 *tri_flt;    // 3 per triangle, 48 B stride: the sweep filter's record {n', g1} {e2, g2} {m, 0} (tri_filter_sweep)
 	const float4 *tri_n;      // 3 per triangle: object-space vertex normals (cold: winner only)
 	const float4 *model_xf;   // 4 per shape slot: model matrix columns      (cold)
 	const float4 *materials;  // 4 per material: the reference's 64-byte record as 4 x float4
@@ -104,6 +105,28 @@ __device__ __forceinline__ void tri_exact(const float4 v0, const float4 e1, cons
 		hit.shape = shape;
 		hit.tri = tri;
 	}
+}
+// The filter of the dense sweep decides the same u-range question from PRE-MULTIPLIED operands.  By the cyclic
+// identities of the triple product,
+//   det = e1 . (d x e2) = d . n',  n' = e2 x e1           su = (o - v0) . (d x e2) = e2 . (o x d) - d . m,  m = e2 x v0
+// so with n', m stored per triangle and c = o x d computed once per ray, det and su cost 9 multiply-adds instead
+// of the 22 operations of tri_filter.  These values differ from the reference's det / su by rounding only, by at
+// most   |d det| <= 22u |e1||e2|   and   |d su| <= 25u |e2| (|o| + |v0|)   (u = 2^-24, DESIGN.md "Triangle
+// filter" derives the bounds), so the reject thresholds are widened by
+//   M = g1 * |o|_1 + g2,   g1 = 48u |e2|_1,   g2 = g1 |v0|_1 + 128u |e1|_1 |e2|_1 + 2e-6
+// which covers both error terms (three times the det term, so that a wrong sign of a near-zero det is harmless
+// too).  A triangle is dropped only when the reference's u test is certain to fail; NaNs compare false and
+// survive; every survivor runs tri_exact on the reference operands.
+//   f0 = {n'.xyz, g1}  f1 = {e2.xyz, g2}  f2 = {m.xyz, -}      rd = {d.xyz, |o|_1}  rc = {c.xyz, -}
+__device__ __forceinline__ bool tri_filter_sweep(const float4 f0, const float4 f1, const float4 f2, const float4 rd,
+                                                 const float4 rc) {
+	float det = fma_(rd.z, f0.z, fma_(rd.y, f0.y, rd.x * f0.x));
+	float t = fma_(rd.z, f2.z, fma_(rd.y, f2.y, rd.x * f2.x));
+	float su = fma_(f1.z, rc.z, fma_(f1.y, rc.y, fma_(f1.x, rc.x, -t)));
+	float x = __int_as_float(__float_as_int(su) ^ (__float_as_int(det) & 0x80000000));
+	float m = fma_(f0.w, rd.w, f1.w);
+	float lim = fma_(fabsf(det), 1.000002f, m);
+	return !(x > lim || x < -m);
 }
 __device__ __forceinline__ void test_triangle(const float4 v0, const float4 e1, const float4 e2, vec3 o, vec3 d,
                                               int shape, int tri, Hit &hit) {
@@ -393,7 +416,8 @@ __device__ __forceinline__ void triangle_phase(const DevScene &sc, int n, int tr
 	const unsigned FULL = 0xffffffffu;
 	const float4 *tiles = wsmem;
 	float4 *rays = wsmem + RING_BYTES / 16;
-	const char *src = reinterpret_cast<const char *>(sc.tri_hot + 3 * (size_t)tri_begin);
+	const char *src = reinterpret_cast<const char *>(sc.tri_flt + 3 * (size_t)tri_begin);
+	const float4 *exact = sc.tri_hot + 3 * (size_t)tri_begin;  // survivors fetch the reference operands from L1/L2
 	const int ntiles = (n + TILE_TRIS - 1) / TILE_TRIS;
 	auto issue = [&](int t) {
 		const int st = t % TILE_STAGES;
@@ -402,9 +426,10 @@ __device__ __forceinline__ void triangle_phase(const DevScene &sc, int n, int tr
 	};
 	if (lane == 0)
 		for (int t = 0; t < min(ntiles, TILE_STAGES); ++t) issue(t);
-	if (active) {
-		rays[2 * lane] = make_float4(o.x, o.y, o.z, 0.f);
-		rays[2 * lane + 1] = make_float4(d.x, d.y, d.z, 0.f);
+	if (active) {  // per-ray operands of the filter: d, |o|_1 and c = o x d
+		const vec3 c = cross(o, d);
+		rays[2 * lane] = make_float4(d.x, d.y, d.z, fabsf(o.x) + fabsf(o.y) + fabsf(o.z));
+		rays[2 * lane + 1] = make_float4(c.x, c.y, c.z, 0.f);
 	}
 	const unsigned ray_mask = __ballot_sync(FULL, active);
 	__syncwarp();
@@ -416,12 +441,12 @@ __device__ __forceinline__ void triangle_phase(const DevScene &sc, int n, int tr
 		const float4 *tile = tiles + st * (TILE_TRIS * 3);
 		const int cnt = min(TILE_TRIS, n - t * TILE_TRIS);
 		// my triangles of this tile: slot q holds triangle q*32 + lane (bit `lane` of the slot's vote)
-		float4 tv0[TRIS_PER_LANE], te1[TRIS_PER_LANE], te2[TRIS_PER_LANE];
+		float4 tf0[TRIS_PER_LANE], tf1[TRIS_PER_LANE], tf2[TRIS_PER_LANE];
 		uint32_t valid[TRIS_PER_LANE];  // beyond the list the tile holds stale shared memory: votes are masked
 #pragma unroll
 		for (int q = 0; q < TRIS_PER_LANE; ++q) {
 			const int j = q * 32 + lane;
-			tv0[q] = tile[3 * j], te1[q] = tile[3 * j + 1], te2[q] = tile[3 * j + 2];
+			tf0[q] = tile[3 * j], tf1[q] = tile[3 * j + 1], tf2[q] = tile[3 * j + 2];
 			const int left = cnt - q * 32;
 			valid[q] = left >= 32 ? 0xffffffffu : (left <= 0 ? 0u : (1u << left) - 1u);
 		}
@@ -430,11 +455,10 @@ __device__ __forceinline__ void triangle_phase(const DevScene &sc, int n, int tr
 		for (int q = 0; q < TRIS_PER_LANE; ++q) cand[q] = 0;
 		for (unsigned rm = ray_mask; rm; rm &= rm - 1) {  // warp-uniform loop over the parked rays
 			const int r = __ffs(rm) - 1;
-			const float4 ro4 = rays[2 * r], rd4 = rays[2 * r + 1];  // broadcast
-			const vec3 ro = xyz(ro4), rd = xyz(rd4);
+			const float4 rd4 = rays[2 * r], rc4 = rays[2 * r + 1];  // broadcast
 #pragma unroll
 			for (int q = 0; q < TRIS_PER_LANE; ++q) {
-				const unsigned v = __ballot_sync(FULL, tri_filter(tv0[q], te1[q], te2[q], ro, rd));
+				const unsigned v = __ballot_sync(FULL, tri_filter_sweep(tf0[q], tf1[q], tf2[q], rd4, rc4));
 				if (lane == r) cand[q] = v;
 			}
 		}
@@ -457,8 +481,8 @@ __device__ __forceinline__ void triangle_phase(const DevScene &sc, int n, int tr
 #pragma unroll
 				for (int q = 0; q < TRIS_PER_LANE; ++q)
 					if (q == j) cand[q] = c & (c - 1);
-				j = j * 32 + bit;
-				tri_exact(tile[3 * j], tile[3 * j + 1], tile[3 * j + 2], o, d, shape, tri_begin + t * TILE_TRIS + j, hit);
+				j = t * TILE_TRIS + j * 32 + bit;
+				tri_exact(__ldg(exact + 3 * j), __ldg(exact + 3 * j + 1), __ldg(exact + 3 * j + 2), o, d, shape, tri_begin + j, hit);
 			}
 		}
 		__syncwarp();  // every lane is done reading this stage before it is refilled
@@ -831,7 +855,7 @@ struct ModelSpan {
 __global__ void __launch_bounds__(256)
 prepare_triangles_kernel(const float4 *__restrict__ aos /* 6 float4 per triangle */, const ModelSpan *__restrict__ spans,
                          int n_spans, int total, const float4 *__restrict__ model_xf, float4 *__restrict__ hot_out,
-                         float4 *__restrict__ n_out) {
+                         float4 *__restrict__ flt_out, float4 *__restrict__ n_out) {
 	int g = blockIdx.x * blockDim.x + threadIdx.x;
 	if (g >= total) return;
 	int lo = 0, hi = n_spans - 1;  // last span with dst_begin <= g
@@ -856,6 +880,16 @@ prepare_triangles_kernel(const float4 *__restrict__ aos /* 6 float4 per triangle
 	hot_out[3 * (size_t)g + 0] = make_float4(w[0].x, w[0].y, w[0].z, 0.f);
 	hot_out[3 * (size_t)g + 1] = make_float4(e1.x, e1.y, e1.z, 0.f);
 	hot_out[3 * (size_t)g + 2] = make_float4(e2.x, e2.y, e2.z, 0.f);
+	// filter record of the dense sweep (tri_filter_sweep): n' = e2 x e1, m = e2 x v0, margins g1, g2
+	const vec3 np = cross(e2, e1), m = cross(e2, w[0]);
+	const float U = 5.9604644775390625e-8f;  // 2^-24
+	const float n1e1 = fabsf(e1.x) + fabsf(e1.y) + fabsf(e1.z), n1e2 = fabsf(e2.x) + fabsf(e2.y) + fabsf(e2.z);
+	const float n1v0 = fabsf(w[0].x) + fabsf(w[0].y) + fabsf(w[0].z);
+	const float g1 = 48.0f * U * n1e2;
+	const float g2 = g1 * n1v0 + 128.0f * U * (n1e1 * n1e2) + 2e-6f;
+	flt_out[3 * (size_t)g + 0] = make_float4(np.x, np.y, np.z, g1);
+	flt_out[3 * (size_t)g + 1] = make_float4(e2.x, e2.y, e2.z, g2);
+	flt_out[3 * (size_t)g + 2] = make_float4(m.x, m.y, m.z, 0.f);
 }
 
 // ---- device math self-test -------------------------------------------------------------------

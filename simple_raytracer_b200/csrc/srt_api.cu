@@ -75,7 +75,7 @@ struct srt_tracer {
 
 	DevBuf<int4> shape_hdr;
 	DevBuf<float4> shape_a, shape_b, model_xf, materials;
-	DevBuf<float4> tri_aos, tri_hot, tri_n;
+	DevBuf<float4> tri_aos, tri_hot, tri_flt, tri_n;
 	DevBuf<float4> scratch;  // one float4 per (pixel, sample) of a launch
 	DevBuf<srt::ModelSpan> spans;
 	size_t n_shapes = 0, n_materials = 0, n_soa_tris = 0;
@@ -124,6 +124,7 @@ srt::DevScene dev_scene(const srt_tracer *t) {
 	s.shape_a = t->shape_a.ptr;
 	s.shape_b = t->shape_b.ptr;
 	s.tri_hot = t->tri_hot.ptr;
+	s.tri_flt = t->tri_flt.ptr;
 	s.tri_n = t->tri_n.ptr;
 	s.model_xf = t->model_xf.ptr;
 	s.materials = t->materials.ptr;
@@ -296,7 +297,7 @@ int srt_destroy(srt_tracer *t) {
 	cudaFree(t->counters);
 	cudaFree(t->sky);
 	t->shape_hdr.release(), t->shape_a.release(), t->shape_b.release(), t->model_xf.release(), t->materials.release();
-	t->tri_aos.release(), t->tri_hot.release(), t->tri_n.release(), t->spans.release(), t->scratch.release();
+	t->tri_aos.release(), t->tri_hot.release(), t->tri_flt.release(), t->tri_n.release(), t->spans.release(), t->scratch.release();
 	if (t->stream) cudaStreamDestroy(t->stream);
 	delete t;
 	return SRT_OK;
@@ -352,6 +353,7 @@ int srt_upload_scene(srt_tracer *t, const srt_shape *shapes, size_t n_shapes, co
 	SRT_CUDA(t, t->materials.reserve(4 * n_materials));
 	SRT_CUDA(t, t->tri_aos.reserve(6 * n_triangles));
 	SRT_CUDA(t, t->tri_hot.reserve(3 * soa));
+	SRT_CUDA(t, t->tri_flt.reserve(3 * soa));
 	SRT_CUDA(t, t->tri_n.reserve(3 * soa));
 	SRT_CUDA(t, t->spans.reserve(spans.size()));
 	cudaStream_t st = t->stream;
@@ -371,7 +373,7 @@ int srt_upload_scene(srt_tracer *t, const srt_shape *shapes, size_t n_shapes, co
 		SRT_CUDA(t, cudaMemcpyAsync(t->spans.ptr, spans.data(), spans.size() * sizeof(srt::ModelSpan), cudaMemcpyHostToDevice, st));
 		const int total = (int)soa;
 		srt::prepare_triangles_kernel<<<(total + 255) / 256, 256, 0, st>>>(t->tri_aos.ptr, t->spans.ptr, (int)spans.size(), total,
-		                                                                  t->model_xf.ptr, t->tri_hot.ptr, t->tri_n.ptr);
+		                                                                  t->model_xf.ptr, t->tri_hot.ptr, t->tri_flt.ptr, t->tri_n.ptr);
 		SRT_CUDA(t, cudaGetLastError());
 	}
 	SRT_CUDA(t, cudaStreamSynchronize(st));  // copy-in semantics, like the blocking writes of tracer.cpp:76-86
