@@ -28,7 +28,8 @@ struct DevScene {
 	const float4 *shape_a;    // sphere {c.xyz, r} | plane {p0.xyz, -} | model {bmin.xyz, -}
 	const float4 *shape_b;    // sphere {-}        | plane {n.xyz, -}  | model {bmax.xyz, -}
 	const float4 *tri_hot;    // 3 per triangle, 48 B stride: world-space v0, e1 = v1-v0, e2 = v2-v0 (+1 pad triangle)
-	const float4 *tri_flt;    // 3 per triangle, 48 B stride: the sweep filter's record {n', g1} {e2, g2} {m, 0} (tri_filter_sweep)
+	const float2 *tri_flt;    // 5 per triangle, 40 B stride: the sweep filter's record n', g, e2, m (tri_filter_sweep)
+	const float *model_k;     // per shape slot: max over the model's triangles of |v0|_1 + 3 |e1|_1 (filter margin)
 	const float4 *tri_n;      // 3 per triangle: object-space vertex normals (cold: winner only)
 	const float4 *model_xf;   // 4 per shape slot: model matrix columns      (cold)
 	const float4 *materials;  // 4 per material: the reference's 64-byte record as 4 x float4
@@ -111,20 +112,31 @@ __device__ __forceinline__ void tri_exact(const float4 v0, const float4 e1, cons
 //   det = e1 . (d x e2) = d . n',  n' = e2 x e1           su = (o - v0) . (d x e2) = e2 . (o x d) - d . m,  m = e2 x v0
 // so with n', m stored per triangle and c = o x d computed once per ray, det and su cost 9 multiply-adds instead
 // of the 22 operations of tri_filter.  These values differ from the reference's det / su by rounding only, by at
-// most   |d det| <= 22u |e1||e2|   and   |d su| <= 25u |e2| (|o| + |v0|)   (u = 2^-24, DESIGN.md "Triangle
+// most   |d det| <= 22u |e1||e2|   and   |d su| <= 25u |e2| (|o| + |v0|)   (u = 2^-24; DESIGN.md "Triangle
 // filter" derives the bounds), so the reject thresholds are widened by
-//   M = g1 * |o|_1 + g2,   g1 = 48u |e2|_1,   g2 = g1 |v0|_1 + 128u |e1|_1 |e2|_1 + 2e-6
-// which covers both error terms (three times the det term, so that a wrong sign of a near-zero det is harmless
-// too).  A triangle is dropped only when the reference's u test is certain to fail; NaNs compare false and
-// survive; every survivor runs tri_exact on the reference operands.
-//   f0 = {n'.xyz, g1}  f1 = {e2.xyz, g2}  f2 = {m.xyz, -}      rd = {d.xyz, |o|_1}  rc = {c.xyz, -}
-__device__ __forceinline__ bool tri_filter_sweep(const float4 f0, const float4 f1, const float4 f2, const float4 rd,
-                                                 const float4 rc) {
-	float det = fma_(rd.z, f0.z, fma_(rd.y, f0.y, rd.x * f0.x));
-	float t = fma_(rd.z, f2.z, fma_(rd.y, f2.y, rd.x * f2.x));
-	float su = fma_(f1.z, rc.z, fma_(f1.y, rc.y, fma_(f1.x, rc.x, -t)));
+//   M = g * R + 2e-6,   g = 48u |e2|_1 (per triangle),   R = |o|_1 + K (per ray),   K = max_model(|v0|_1 + 3 |e1|_1)
+// which covers both error terms (the det term three times over, so that a wrong sign of a near-zero det is
+// harmless too).  A triangle is dropped only when the reference's u test is certain to fail; NaNs compare false
+// and survive; every survivor runs tri_exact on the reference operands.
+//   record (40 B): a = {n'.x, n'.y}  b = {n'.z, g}  c = {e2.x, e2.y}  e = {e2.z, m.x}  f = {m.y, m.z}
+//   ray: rd = {d.xyz, R}  rc = {(o x d).xyz, -}
+struct TriFlt {
+	float2 a, b, c, e, f;
+};
+#ifndef SRT_SWEEP_RMAX
+#define SRT_SWEEP_RMAX 1
+#endif
+#ifndef SRT_PREFETCH_EXACT
+#define SRT_PREFETCH_EXACT 0
+#endif
+// With SRT_SWEEP_RMAX the margin is formed once per triangle and tile from the LARGEST R among the parked rays
+// (r.b.y then already holds M = g * Rmax + 2e-6): a larger margin only lets more triangles through.
+__device__ __forceinline__ bool tri_filter_sweep(const TriFlt &r, const float4 rd, const float4 rc) {
+	float det = fma_(rd.z, r.b.x, fma_(rd.y, r.a.y, rd.x * r.a.x));
+	float t = fma_(rd.z, r.f.y, fma_(rd.y, r.f.x, rd.x * r.e.y));
+	float su = fma_(r.e.x, rc.z, fma_(r.c.y, rc.y, fma_(r.c.x, rc.x, -t)));
 	float x = __int_as_float(__float_as_int(su) ^ (__float_as_int(det) & 0x80000000));
-	float m = fma_(f0.w, rd.w, f1.w);
+	float m = SRT_SWEEP_RMAX ? r.b.y : fma_(r.b.y, rd.w, 2e-6f);
 	float lim = fma_(fabsf(det), 1.000002f, m);
 	return !(x > lim || x < -m);
 }
@@ -380,11 +392,16 @@ constexpr int RENDER_THREADS = SRT_RENDER_THREADS;
 constexpr int TRIS_PER_LANE = SRT_TRIS_PER_LANE;
 constexpr int TILE_TRIS = 32 * TRIS_PER_LANE;
 constexpr int TILE_STAGES = SRT_TILE_STAGES;
-constexpr int TILE_BYTES = TILE_TRIS * 48;
+constexpr int FLT_BYTES = 40;                 // filter record of one triangle (TriFlt)
+constexpr int TILE_BYTES = TILE_TRIS * FLT_BYTES;
 constexpr int RING_BYTES = TILE_STAGES * TILE_BYTES;
-constexpr int RAYS_BYTES = 32 * 32;  // 32 rays x (origin float4, direction float4)
+constexpr int RAYS_BYTES = 32 * 48;           // 32 rays x {d, R} {o x d, -} {o, -}
+constexpr int PAIR_SLOTS = 256;               // ring of filter survivors (ray << 27 | triangle) awaiting the exact test
+constexpr int PAIRS_BYTES = PAIR_SLOTS * 4;
+constexpr int BEST_BYTES = 32 * 8;            // per parked ray: (t bits << 32 | triangle + 1), minimised atomically
 constexpr int RENDER_WARPS = RENDER_THREADS / 32;
-constexpr int WARP_SMEM_BYTES = RING_BYTES + RAYS_BYTES;
+constexpr int WARP_SMEM_BYTES = RING_BYTES + RAYS_BYTES + PAIRS_BYTES + BEST_BYTES;
+constexpr int MAX_SWEEP_TRIS = 1 << 27;       // a pair packs the triangle's index within its model in 27 bits
 constexpr int RENDER_SMEM_BYTES = RENDER_WARPS * (WARP_SMEM_BYTES + TILE_STAGES * 8);
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -409,85 +426,160 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 	    : "memory");
 }
 
+// Exact test of one filter survivor by whichever lane picked it up: the reference arithmetic (tri_exact) on the
+// reference operands, fetched through L1/L2.  A hit is folded into best[ray] with an atomic min on
+// (t bits << 32 | triangle + 1): for positive floats the bit pattern orders like the value, so the minimum is the
+// closest hit and, among equal t, the lowest triangle index -- what the sequential loop of render.cl:324-350
+// with its strict `t_i < tmin` keeps.  best[ray] starts at (hit.t << 32 | 0), so an equal t never replaces the hit
+// of an earlier shape either.
+__device__ __forceinline__ void exact_pair(const float4 v0, const float4 e1, const float4 e2, const float4 o4,
+                                           const float4 d4, unsigned long long *best_slot, int tri_local) {
+	Hit h = {__int_as_float(0x7f800000), -1, -1};
+	tri_exact(v0, e1, e2, xyz(o4), xyz(d4), 0, tri_local, h);
+	if (h.shape == 0) {
+		const unsigned long long key = ((unsigned long long)__float_as_uint(h.t) << 32) | (unsigned)(tri_local + 1);
+		if (key < *best_slot) atomicMin(best_slot, key);
+	}
+}
+
 // n, tri_begin, shape: the model being swept (warp-uniform); active: this lane's ray is parked at it.
 __device__ __forceinline__ void triangle_phase(const DevScene &sc, int n, int tri_begin, int shape, bool active, vec3 o,
-                                               vec3 d, Hit &hit, float4 *wsmem, uint32_t wsmem_s, uint32_t bars_s,
+                                               vec3 d, Hit &hit, unsigned char *wsmem, uint32_t wsmem_s, uint32_t bars_s,
                                                uint32_t &parity, int lane) {
 	const unsigned FULL = 0xffffffffu;
-	const float4 *tiles = wsmem;
-	float4 *rays = wsmem + RING_BYTES / 16;
-	const char *src = reinterpret_cast<const char *>(sc.tri_flt + 3 * (size_t)tri_begin);
+	const unsigned char *tiles = wsmem;
+	float4 *rays = reinterpret_cast<float4 *>(wsmem + RING_BYTES);
+	uint32_t *pairs = reinterpret_cast<uint32_t *>(wsmem + RING_BYTES + RAYS_BYTES);
+	unsigned long long *best = reinterpret_cast<unsigned long long *>(wsmem + RING_BYTES + RAYS_BYTES + PAIRS_BYTES);
+	const char *src = reinterpret_cast<const char *>(sc.tri_flt + 5 * (size_t)tri_begin);  // tri_begin is even: 16 B aligned
 	const float4 *exact = sc.tri_hot + 3 * (size_t)tri_begin;  // survivors fetch the reference operands from L1/L2
 	const int ntiles = (n + TILE_TRIS - 1) / TILE_TRIS;
 	auto issue = [&](int t) {
 		const int st = t % TILE_STAGES;
-		bulk_load_tile(wsmem_s + st * TILE_BYTES, src + (size_t)t * TILE_BYTES, (uint32_t)min(TILE_TRIS, n - t * TILE_TRIS) * 48u,
-		               bars_s + st * 8);
+		const uint32_t bytes = ((uint32_t)min(TILE_TRIS, n - t * TILE_TRIS) * FLT_BYTES + 15u) & ~15u;  // the array is padded
+		bulk_load_tile(wsmem_s + st * TILE_BYTES, src + (size_t)t * TILE_BYTES, bytes, bars_s + st * 8);
 	};
 	if (lane == 0)
 		for (int t = 0; t < min(ntiles, TILE_STAGES); ++t) issue(t);
-	if (active) {  // per-ray operands of the filter: d, |o|_1 and c = o x d
+	if (active) {  // per-ray operands: d, R = |o|_1 + K, c = o x d for the filter; o for the exact test
 		const vec3 c = cross(o, d);
-		rays[2 * lane] = make_float4(d.x, d.y, d.z, fabsf(o.x) + fabsf(o.y) + fabsf(o.z));
-		rays[2 * lane + 1] = make_float4(c.x, c.y, c.z, 0.f);
+		rays[3 * lane] = make_float4(d.x, d.y, d.z, fabsf(o.x) + fabsf(o.y) + fabsf(o.z) + __ldg(&sc.model_k[shape]));
+		rays[3 * lane + 1] = make_float4(c.x, c.y, c.z, 0.f);
+		rays[3 * lane + 2] = make_float4(o.x, o.y, o.z, 0.f);
+		best[lane] = (unsigned long long)__float_as_uint(hit.t) << 32;
 	}
 	const unsigned ray_mask = __ballot_sync(FULL, active);
+	int pair_head = 0, pair_count = 0;  // warp-uniform
+	float rmax = active ? rays[3 * lane].w : 0.0f;  // NaN (a ray the filter cannot decide) must win the max
+	if (SRT_SWEEP_RMAX) {
+#pragma unroll
+		for (int off = 16; off > 0; off >>= 1) {
+			const float other = __shfl_xor_sync(FULL, rmax, off);
+			rmax = (other > rmax || other != other) ? other : rmax;
+		}
+	}
 	__syncwarp();
 
-	for (int t = 0; t < ntiles; ++t) {
-		const int st = t % TILE_STAGES;
-		mbar_wait(bars_s + st * 8, (parity >> st) & 1u);
-		parity ^= 1u << st;
-		const float4 *tile = tiles + st * (TILE_TRIS * 3);
-		const int cnt = min(TILE_TRIS, n - t * TILE_TRIS);
-		// my triangles of this tile: slot q holds triangle q*32 + lane (bit `lane` of the slot's vote)
-		float4 tf0[TRIS_PER_LANE], tf1[TRIS_PER_LANE], tf2[TRIS_PER_LANE];
-		uint32_t valid[TRIS_PER_LANE];  // beyond the list the tile holds stale shared memory: votes are masked
-#pragma unroll
-		for (int q = 0; q < TRIS_PER_LANE; ++q) {
-			const int j = q * 32 + lane;
-			tf0[q] = tile[3 * j], tf1[q] = tile[3 * j + 1], tf2[q] = tile[3 * j + 2];
-			const int left = cnt - q * 32;
-			valid[q] = left >= 32 ? 0xffffffffu : (left <= 0 ? 0u : (1u << left) - 1u);
-		}
+	// Code size matters here (the kernel's instruction footprint must stay cache resident while warps sit in
+	// different phases), so there is ONE instance of the exact test: the loop below drains the ring 32 pairs at a
+	// time, and every path that produces survivors -- including a ray the filter cannot decide at all -- feeds
+	// the ring.
+	for (int t = 0; t <= ntiles; ++t) {
 		uint32_t cand[TRIS_PER_LANE];
 #pragma unroll
 		for (int q = 0; q < TRIS_PER_LANE; ++q) cand[q] = 0;
-		for (unsigned rm = ray_mask; rm; rm &= rm - 1) {  // warp-uniform loop over the parked rays
-			const int r = __ffs(rm) - 1;
-			const float4 rd4 = rays[2 * r], rc4 = rays[2 * r + 1];  // broadcast
+		if (t < ntiles) {
+			const int st = t % TILE_STAGES;
+			mbar_wait(bars_s + st * 8, (parity >> st) & 1u);
+			parity ^= 1u << st;
+			const float2 *tile = reinterpret_cast<const float2 *>(tiles + st * TILE_BYTES);
+			// my triangles of this tile: slot q holds triangle q*32 + lane (bit `lane` of the slot's vote)
+			TriFlt tf[TRIS_PER_LANE];
 #pragma unroll
 			for (int q = 0; q < TRIS_PER_LANE; ++q) {
-				const unsigned v = __ballot_sync(FULL, tri_filter_sweep(tf0[q], tf1[q], tf2[q], rd4, rc4));
-				if (lane == r) cand[q] = v;
+				const float2 *r = tile + 5 * (q * 32 + lane);  // 40 B stride: conflict-free LDS.64
+				tf[q].a = r[0], tf[q].b = r[1], tf[q].c = r[2], tf[q].e = r[3], tf[q].f = r[4];
+				if (SRT_SWEEP_RMAX) tf[q].b.y = fma_(tf[q].b.y, rmax, 2e-6f);
+			}
+			for (unsigned rm = ray_mask; rm; rm &= rm - 1) {  // warp-uniform loop over the parked rays
+				const int r = __ffs(rm) - 1;
+				const float4 rd4 = rays[3 * r], rc4 = rays[3 * r + 1];  // broadcast
+#pragma unroll
+				for (int q = 0; q < TRIS_PER_LANE; ++q) {
+					const unsigned v = __ballot_sync(FULL, tri_filter_sweep(tf[q], rd4, rc4));
+					if (lane == r) cand[q] = v;
+				}
+			}
+			__syncwarp();  // every lane is done reading this stage before it is refilled
+			if (lane == 0 && t + TILE_STAGES < ntiles) issue(t + TILE_STAGES);
+			// beyond the end of the list the tile holds stale shared memory: those votes are masked
+			const int cnt = n - t * TILE_TRIS;
+#pragma unroll
+			for (int q = 0; q < TRIS_PER_LANE; ++q) {
+				const int left = cnt - q * 32;
+				cand[q] &= left >= 32 ? 0xffffffffu : (left <= 0 ? 0u : (1u << left) - 1u);
 			}
 		}
-		if (active) {
-			// exact test of my ray's survivors, lowest triangle index first; ONE loop over all slots so the
-			// warp iterates max-over-lanes(total survivors) times, not once per slot
+		// survivors -> pair ring -> exact tests, 32 at a time; after the last tile (t == ntiles) the ring is emptied
+		for (;;) {
+			int mine = 0;
 #pragma unroll
-			for (int q = 0; q < TRIS_PER_LANE; ++q) cand[q] &= valid[q];
-			for (;;) {
-				int j = -1;
+			for (int q = 0; q < TRIS_PER_LANE; ++q) mine += __popc(cand[q]);
+			int incl = mine;  // inclusive prefix sum over the lanes
 #pragma unroll
-				for (int q = TRIS_PER_LANE - 1; q >= 0; --q)
-					if (cand[q]) j = q;
-				if (j < 0) break;
-				uint32_t c = 0;
-#pragma unroll
-				for (int q = 0; q < TRIS_PER_LANE; ++q)
-					if (q == j) c = cand[q];
-				const int bit = __ffs(c) - 1;
-#pragma unroll
-				for (int q = 0; q < TRIS_PER_LANE; ++q)
-					if (q == j) cand[q] = c & (c - 1);
-				j = t * TILE_TRIS + j * 32 + bit;
-				tri_exact(__ldg(exact + 3 * j), __ldg(exact + 3 * j + 1), __ldg(exact + 3 * j + 2), o, d, shape, tri_begin + j, hit);
+			for (int off = 1; off < 32; off <<= 1) {
+				const int up = __shfl_up_sync(FULL, incl, off);
+				if (lane >= off) incl += up;
 			}
+			const int total = __shfl_sync(FULL, incl, 31);
+			const int room = PAIR_SLOTS - pair_count;
+			if (total) {
+				int rank = incl - mine;  // my first survivor's rank among the warp's
+#pragma unroll
+				for (int q = 0; q < TRIS_PER_LANE; ++q) {
+					uint32_t c = cand[q];
+					const uint32_t base = ((uint32_t)lane << 27) | (uint32_t)(t * TILE_TRIS + q * 32);
+					while (c && rank < room) {
+						if (SRT_PREFETCH_EXACT) {
+							const float4 *pf = exact + 3 * (size_t)(t * TILE_TRIS + q * 32 + (__ffs(c) - 1));
+							asm volatile("prefetch.global.L1 [%0];" ::"l"(pf));
+							asm volatile("prefetch.global.L1 [%0];" ::"l"(pf + 2));
+						}
+						pairs[(pair_head + pair_count + rank) & (PAIR_SLOTS - 1)] = base + (__ffs(c) - 1);
+						c &= c - 1;
+						++rank;
+					}
+					cand[q] = c;  // what did not fit waits for the next round
+				}
+				pair_count += min(total, room);
+				__syncwarp();
+			}
+			const bool flush = t == ntiles || total > room;
+			while (pair_count >= 32 || (flush && pair_count > 0)) {
+				const int m = min(pair_count, 32);
+				if (lane < m) {
+					const uint32_t pr = pairs[(pair_head + lane) & (PAIR_SLOTS - 1)];
+					const int r = pr >> 27, j = pr & (MAX_SWEEP_TRIS - 1);
+					exact_pair(__ldg(exact + 3 * (size_t)j), __ldg(exact + 3 * (size_t)j + 1), __ldg(exact + 3 * (size_t)j + 2),
+					           rays[3 * r + 2], rays[3 * r], best + r, j);
+				}
+				pair_head = (pair_head + m) & (PAIR_SLOTS - 1);
+				pair_count -= m;
+				__syncwarp();
+			}
+			if (total <= room) break;
 		}
-		__syncwarp();  // every lane is done reading this stage before it is refilled
-		if (lane == 0 && t + TILE_STAGES < ntiles) issue(t + TILE_STAGES);
 	}
+	if (active) {
+		const unsigned long long k = best[lane];
+		const unsigned tri1 = (unsigned)k;
+		if (tri1) {
+			hit.t = __uint_as_float((unsigned)(k >> 32));
+			hit.shape = shape;
+			hit.tri = tri_begin + (int)tri1 - 1;
+		}
+	}
+	__syncwarp();
 }
 
 // Start the camera path of work item `item` = local_pixel * num_samples + sample (render.cl:488-516).
@@ -538,7 +630,7 @@ render_kernel(const __grid_constant__ RenderParams p, const __grid_constant__ De
 	// per-warp ring of triangle tiles + one mbarrier per stage
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	const int warp = threadIdx.x >> 5;
-	float4 *wsmem = reinterpret_cast<float4 *>(smem_raw + warp * WARP_SMEM_BYTES);
+	unsigned char *wsmem = smem_raw + warp * WARP_SMEM_BYTES;
 	const uint32_t wsmem_s = smem_u32(wsmem);
 	const uint32_t bars_s = smem_u32(smem_raw + RENDER_WARPS * WARP_SMEM_BYTES + warp * (TILE_STAGES * 8));
 	uint32_t parity = 0;
@@ -855,7 +947,7 @@ struct ModelSpan {
 __global__ void __launch_bounds__(256)
 prepare_triangles_kernel(const float4 *__restrict__ aos /* 6 float4 per triangle */, const ModelSpan *__restrict__ spans,
                          int n_spans, int total, const float4 *__restrict__ model_xf, float4 *__restrict__ hot_out,
-                         float4 *__restrict__ flt_out, float4 *__restrict__ n_out) {
+                         float2 *__restrict__ flt_out, float *__restrict__ model_k, float4 *__restrict__ n_out) {
 	int g = blockIdx.x * blockDim.x + threadIdx.x;
 	if (g >= total) return;
 	int lo = 0, hi = n_spans - 1;  // last span with dst_begin <= g
@@ -865,6 +957,7 @@ prepare_triangles_kernel(const float4 *__restrict__ aos /* 6 float4 per triangle
 		else hi = mid - 1;
 	}
 	const ModelSpan sp = spans[lo];
+	if (g - sp.dst_begin >= sp.count) return;  // alignment gap between two models' ranges
 	const float4 *tri = aos + 6 * (size_t)(sp.src_begin + (g - sp.dst_begin));
 	const float4 m0 = model_xf[4 * sp.shape + 0], m1 = model_xf[4 * sp.shape + 1];
 	const float4 m2 = model_xf[4 * sp.shape + 2], m3 = model_xf[4 * sp.shape + 3];
@@ -880,16 +973,19 @@ prepare_triangles_kernel(const float4 *__restrict__ aos /* 6 float4 per triangle
 	hot_out[3 * (size_t)g + 0] = make_float4(w[0].x, w[0].y, w[0].z, 0.f);
 	hot_out[3 * (size_t)g + 1] = make_float4(e1.x, e1.y, e1.z, 0.f);
 	hot_out[3 * (size_t)g + 2] = make_float4(e2.x, e2.y, e2.z, 0.f);
-	// filter record of the dense sweep (tri_filter_sweep): n' = e2 x e1, m = e2 x v0, margins g1, g2
+	// filter record of the dense sweep (tri_filter_sweep): n' = e2 x e1, m = e2 x v0, margin scale g; the model's K
 	const vec3 np = cross(e2, e1), m = cross(e2, w[0]);
 	const float U = 5.9604644775390625e-8f;  // 2^-24
 	const float n1e1 = fabsf(e1.x) + fabsf(e1.y) + fabsf(e1.z), n1e2 = fabsf(e2.x) + fabsf(e2.y) + fabsf(e2.z);
 	const float n1v0 = fabsf(w[0].x) + fabsf(w[0].y) + fabsf(w[0].z);
-	const float g1 = 48.0f * U * n1e2;
-	const float g2 = g1 * n1v0 + 128.0f * U * (n1e1 * n1e2) + 2e-6f;
-	flt_out[3 * (size_t)g + 0] = make_float4(np.x, np.y, np.z, g1);
-	flt_out[3 * (size_t)g + 1] = make_float4(e2.x, e2.y, e2.z, g2);
-	flt_out[3 * (size_t)g + 2] = make_float4(m.x, m.y, m.z, 0.f);
+	float2 *r = flt_out + 5 * (size_t)g;
+	r[0] = make_float2(np.x, np.y);
+	r[1] = make_float2(np.z, 48.0f * U * n1e2);
+	r[2] = make_float2(e2.x, e2.y);
+	r[3] = make_float2(e2.z, m.x);
+	r[4] = make_float2(m.y, m.z);
+	const float k = n1v0 + 3.0f * n1e1;  // non-negative (or NaN, which the filter then passes): orders like its bits
+	atomicMax(reinterpret_cast<unsigned int *>(model_k + sp.shape), __float_as_uint(k == k ? k : __int_as_float(0x7f800000)));
 }
 
 // ---- device math self-test -------------------------------------------------------------------

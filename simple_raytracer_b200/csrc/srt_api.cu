@@ -75,7 +75,9 @@ struct srt_tracer {
 
 	DevBuf<int4> shape_hdr;
 	DevBuf<float4> shape_a, shape_b, model_xf, materials;
-	DevBuf<float4> tri_aos, tri_hot, tri_flt, tri_n;
+	DevBuf<float4> tri_aos, tri_hot, tri_n;
+	DevBuf<float2> tri_flt;  // 5 per SoA triangle (40 B filter records) + 16 B of padding
+	DevBuf<float> model_k;   // per shape slot
 	DevBuf<float4> scratch;  // one float4 per (pixel, sample) of a launch
 	DevBuf<srt::ModelSpan> spans;
 	size_t n_shapes = 0, n_materials = 0, n_soa_tris = 0;
@@ -125,6 +127,7 @@ srt::DevScene dev_scene(const srt_tracer *t) {
 	s.shape_b = t->shape_b.ptr;
 	s.tri_hot = t->tri_hot.ptr;
 	s.tri_flt = t->tri_flt.ptr;
+	s.model_k = t->model_k.ptr;
 	s.tri_n = t->tri_n.ptr;
 	s.model_xf = t->model_xf.ptr;
 	s.materials = t->materials.ptr;
@@ -297,7 +300,7 @@ int srt_destroy(srt_tracer *t) {
 	cudaFree(t->counters);
 	cudaFree(t->sky);
 	t->shape_hdr.release(), t->shape_a.release(), t->shape_b.release(), t->model_xf.release(), t->materials.release();
-	t->tri_aos.release(), t->tri_hot.release(), t->tri_flt.release(), t->tri_n.release(), t->spans.release(), t->scratch.release();
+	t->tri_aos.release(), t->tri_hot.release(), t->tri_flt.release(), t->model_k.release(), t->tri_n.release(), t->spans.release(), t->scratch.release();
 	if (t->stream) cudaStreamDestroy(t->stream);
 	delete t;
 	return SRT_OK;
@@ -336,6 +339,9 @@ int srt_upload_scene(srt_tracer *t, const srt_shape *shapes, size_t n_shapes, co
 			a[i] = make_float4(m.bounding_min.x, m.bounding_min.y, m.bounding_min.z, 0);
 			b[i] = make_float4(m.bounding_max.x, m.bounding_max.y, m.bounding_max.z, 0);
 			for (int c = 0; c < 4; ++c) xf[4 * i + c] = make_float4(m.transform[c].x, m.transform[c].y, m.transform[c].z, m.transform[c].w);
+			if (m.num_triangles > (unsigned)srt::MAX_SWEEP_TRIS)
+				return fail(t, SRT_ERR_INVALID, "shape %zu: %u triangles in one model (limit %d)", i, m.num_triangles, srt::MAX_SWEEP_TRIS);
+			soa = (soa + 1) & ~(size_t)1;  // even start: the 40-byte filter records of a model begin 16-byte aligned
 			hdr[i].z = (int)soa;
 			hdr[i].w = (int)m.num_triangles;
 			if (m.num_triangles) spans.push_back(srt::ModelSpan{(int)i, (int)m.triangle_index, (int)soa, (int)m.num_triangles});
@@ -353,7 +359,8 @@ int srt_upload_scene(srt_tracer *t, const srt_shape *shapes, size_t n_shapes, co
 	SRT_CUDA(t, t->materials.reserve(4 * n_materials));
 	SRT_CUDA(t, t->tri_aos.reserve(6 * n_triangles));
 	SRT_CUDA(t, t->tri_hot.reserve(3 * soa));
-	SRT_CUDA(t, t->tri_flt.reserve(3 * soa));
+	SRT_CUDA(t, t->tri_flt.reserve(5 * soa + 2));
+	SRT_CUDA(t, t->model_k.reserve(n_shapes));
 	SRT_CUDA(t, t->tri_n.reserve(3 * soa));
 	SRT_CUDA(t, t->spans.reserve(spans.size()));
 	cudaStream_t st = t->stream;
@@ -372,8 +379,11 @@ int srt_upload_scene(srt_tracer *t, const srt_shape *shapes, size_t n_shapes, co
 	if (!spans.empty()) {
 		SRT_CUDA(t, cudaMemcpyAsync(t->spans.ptr, spans.data(), spans.size() * sizeof(srt::ModelSpan), cudaMemcpyHostToDevice, st));
 		const int total = (int)soa;
+		SRT_CUDA(t, cudaMemsetAsync(t->model_k.ptr, 0, n_shapes * sizeof(float), st));
+		SRT_CUDA(t, cudaMemsetAsync(t->tri_flt.ptr, 0, (5 * soa + 2) * sizeof(float2), st));  // alignment gaps and the tail pad
 		srt::prepare_triangles_kernel<<<(total + 255) / 256, 256, 0, st>>>(t->tri_aos.ptr, t->spans.ptr, (int)spans.size(), total,
-		                                                                  t->model_xf.ptr, t->tri_hot.ptr, t->tri_flt.ptr, t->tri_n.ptr);
+		                                                                  t->model_xf.ptr, t->tri_hot.ptr, t->tri_flt.ptr,
+		                                                                  t->model_k.ptr, t->tri_n.ptr);
 		SRT_CUDA(t, cudaGetLastError());
 	}
 	SRT_CUDA(t, cudaStreamSynchronize(st));  // copy-in semantics, like the blocking writes of tracer.cpp:76-86
