@@ -126,6 +126,12 @@ struct TriFlt {
 #ifndef SRT_SWEEP_RMAX
 #define SRT_SWEEP_RMAX 1
 #endif
+#ifndef SRT_MARGIN_SCALE  // developer mutation test only: 0 removes the error margins of the sweep filter
+#define SRT_MARGIN_SCALE 1.0f
+#endif
+#ifndef SRT_RAYS_PER_ITER
+#define SRT_RAYS_PER_ITER 2
+#endif
 #ifndef SRT_PREFETCH_EXACT
 #define SRT_PREFETCH_EXACT 0
 #endif
@@ -136,7 +142,7 @@ __device__ __forceinline__ bool tri_filter_sweep(const TriFlt &r, const float4 r
 	float t = fma_(rd.z, r.f.y, fma_(rd.y, r.f.x, rd.x * r.e.y));
 	float su = fma_(r.e.x, rc.z, fma_(r.c.y, rc.y, fma_(r.c.x, rc.x, -t)));
 	float x = __int_as_float(__float_as_int(su) ^ (__float_as_int(det) & 0x80000000));
-	float m = SRT_SWEEP_RMAX ? r.b.y : fma_(r.b.y, rd.w, 2e-6f);
+	float m = SRT_SWEEP_RMAX ? r.b.y : fma_(r.b.y, rd.w, 2e-6f * SRT_MARGIN_SCALE);
 	float lim = fma_(fabsf(det), 1.000002f, m);
 	return !(x > lim || x < -m);
 }
@@ -499,8 +505,32 @@ __device__ __forceinline__ void triangle_phase(const DevScene &sc, int n, int tr
 			for (int q = 0; q < TRIS_PER_LANE; ++q) {
 				const float2 *r = tile + 5 * (q * 32 + lane);  // 40 B stride: conflict-free LDS.64
 				tf[q].a = r[0], tf[q].b = r[1], tf[q].c = r[2], tf[q].e = r[3], tf[q].f = r[4];
-				if (SRT_SWEEP_RMAX) tf[q].b.y = fma_(tf[q].b.y, rmax, 2e-6f);
+				if (SRT_SWEEP_RMAX) tf[q].b.y = fma_(tf[q].b.y, rmax, 2e-6f * SRT_MARGIN_SCALE);
 			}
+#if SRT_RAYS_PER_ITER == 2
+			// two parked rays per trip: half the loop overhead per ray and eight independent dependency chains
+			unsigned rm = ray_mask;
+			for (; rm & (rm - 1); rm &= rm - 1, rm &= rm - 1) {  // warp-uniform; at least two rays left
+				const int r0 = __ffs(rm) - 1, r1 = __ffs(rm & (rm - 1)) - 1;
+				const float4 rd0 = rays[3 * r0], rc0 = rays[3 * r0 + 1], rd1 = rays[3 * r1], rc1 = rays[3 * r1 + 1];
+#pragma unroll
+				for (int q = 0; q < TRIS_PER_LANE; ++q) {
+					const unsigned v0 = __ballot_sync(FULL, tri_filter_sweep(tf[q], rd0, rc0));
+					const unsigned v1 = __ballot_sync(FULL, tri_filter_sweep(tf[q], rd1, rc1));
+					if (lane == r0) cand[q] = v0;
+					if (lane == r1) cand[q] = v1;
+				}
+			}
+			if (rm) {  // odd one out
+				const int r = __ffs(rm) - 1;
+				const float4 rd4 = rays[3 * r], rc4 = rays[3 * r + 1];
+#pragma unroll
+				for (int q = 0; q < TRIS_PER_LANE; ++q) {
+					const unsigned v = __ballot_sync(FULL, tri_filter_sweep(tf[q], rd4, rc4));
+					if (lane == r) cand[q] = v;
+				}
+			}
+#else
 			for (unsigned rm = ray_mask; rm; rm &= rm - 1) {  // warp-uniform loop over the parked rays
 				const int r = __ffs(rm) - 1;
 				const float4 rd4 = rays[3 * r], rc4 = rays[3 * r + 1];  // broadcast
@@ -510,6 +540,7 @@ __device__ __forceinline__ void triangle_phase(const DevScene &sc, int n, int tr
 					if (lane == r) cand[q] = v;
 				}
 			}
+#endif
 			__syncwarp();  // every lane is done reading this stage before it is refilled
 			if (lane == 0 && t + TILE_STAGES < ntiles) issue(t + TILE_STAGES);
 			// beyond the end of the list the tile holds stale shared memory: those votes are masked
@@ -980,7 +1011,7 @@ prepare_triangles_kernel(const float4 *__restrict__ aos /* 6 float4 per triangle
 	const float n1v0 = fabsf(w[0].x) + fabsf(w[0].y) + fabsf(w[0].z);
 	float2 *r = flt_out + 5 * (size_t)g;
 	r[0] = make_float2(np.x, np.y);
-	r[1] = make_float2(np.z, 48.0f * U * n1e2);
+	r[1] = make_float2(np.z, 48.0f * SRT_MARGIN_SCALE * U * n1e2);
 	r[2] = make_float2(e2.x, e2.y);
 	r[3] = make_float2(e2.z, m.x);
 	r[4] = make_float2(m.y, m.z);

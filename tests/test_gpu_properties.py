@@ -290,3 +290,85 @@ def test_rays_through_shared_edges_and_vertices(sky, oracle_lib):
     tr.accumulate(rd)
     want, _ = oracle_lib.render(rd, sc.scene_data, sc.shapes, sc.triangles, sc.materials, sky)
     assert_bit_equal(want, tr.read_canvas(), "grid")
+
+
+def _mesh_scene(tris, xf, cam, name, mats=None, extra_shapes=(), w=160, h=96, ns=2, nb=5):
+    shapes = list(extra_shapes) + [scenes.model(1, tris, 0, len(tris), xf)]
+    mats = mats or [scenes.material((0.8, 0.8, 0.8)),
+                    scenes.material((0.9, 0.6, 0.3), smoothness=0.7, metallic=0.4, specular=0.2)]
+    return scenes.Scene(name, w, h, ns, nb, 1, scenes._stack(shapes, scenes.SHAPE), tris,
+                        scenes._stack(mats, scenes.MATERIAL), cam)
+
+
+def _check_against_oracle(sc, sky, oracle_lib, what, min_mesh_pixels=200, mesh_shape=None):
+    tr = make_tracer(sc, sky)
+    rd = sc.render_data(0)
+    oi, ot = oracle_lib.primary(rd, sc.scene_data, sc.shapes, sc.triangles)
+    gi, gt = tr.debug_primary(rd)
+    assert np.array_equal(oi, gi), f"{what}: {int((oi != gi).sum())} primary ids differ"
+    assert_bit_equal(ot, gt, f"{what}: t")
+    mesh_shape = len(sc.shapes) - 1 if mesh_shape is None else mesh_shape
+    assert (gi == mesh_shape).sum() >= min_mesh_pixels, f"{what}: the mesh is not in view"
+    want, wc = oracle_lib.render(rd, sc.scene_data, sc.shapes, sc.triangles, sc.materials, sky)
+    cnt = tr.accumulate_counted(rd)
+    assert_bit_equal(want, tr.read_canvas(), what)
+    assert [int(v) for v in wc] == [int(cnt[0][n]) for n in cnt.dtype.names]
+
+
+@pytest.mark.parametrize("offset", [(0, 0, 0), (1000.0, -2000.0, 512.0), (-3.0e5, 1.0e5, 2.0e5)])
+def test_sweep_filter_margins_far_from_the_origin(sky, oracle_lib, offset):
+    """The sweep filter works on pre-multiplied operands (o x d, e2 x v0) whose rounding error grows with the
+    distance from the origin; its margins must grow with it.  The same mesh and camera translated far away: the
+    reference's own arithmetic degrades there (o - v0 loses bits), and the CUDA path must degrade identically."""
+    v, n, f = scenes.noisy_icosphere(3, seed=9)
+    tris = scenes.mesh_triangles(v, f, n)
+    off = np.asarray(offset, np.float32)
+    sc = _mesh_scene(tris, scenes.translate(off + (0, 0, -3)) @ scenes.scale(1.2),
+                     scenes.camera_matrix(off + (0, 0.2, 1.5)), f"far{offset}",
+                     extra_shapes=[scenes.plane(0, off + (0, -1.5, 0), (0, 1, 0))])
+    _check_against_oracle(sc, sky, oracle_lib, f"offset {offset}")
+
+
+@pytest.mark.parametrize("size", [1e-4, 1e-2, 1e3])
+def test_sweep_filter_tiny_and_huge_triangles(sky, oracle_lib, size):
+    """Mesh scale from 1e-4 to 1e3 scene units (the absolute 2e-6 slack of the filter dominates at the small end,
+    the relative terms at the large end); the camera distance scales along."""
+    v, n, f = scenes.noisy_icosphere(2, seed=4)
+    tris = scenes.mesh_triangles((v * size).astype(np.float32), f, n)
+    sc = _mesh_scene(tris, scenes.translate((0, 0, -3 * size)), scenes.camera_matrix((0, 0, 0.5 * size)), f"size{size}")
+    _check_against_oracle(sc, sky, oracle_lib, f"size {size}")
+
+
+def test_sweep_filter_undecidable_triangles_overflow_the_pair_ring(sky, oracle_lib):
+    """Hundreds of zero-area triangles (all three vertices equal, or collinear): det = 0, so the filter can decide
+    nothing and every one of them survives -- far more survivors per tile than the pair ring holds -- while the
+    reference rejects them all (render.cl:253).  Real triangles are interleaved so that hits still have to be
+    found in order."""
+    rng = np.random.default_rng(5)
+    v, n, f = scenes.noisy_icosphere(2, seed=6)
+    real = scenes.mesh_triangles(v, f, n)
+    junk = np.zeros(900, scenes.TRIANGLE)
+    p = rng.normal(size=(900, 1, 3)).astype(np.float32) * 0.5
+    junk["v"]["pos"] = np.repeat(p, 3, axis=1)
+    junk["v"]["pos"][::3, 1] += (0.3, 0, 0)          # collinear: v0, v0 + a, v0 + 2a
+    junk["v"]["pos"][::3, 2] += (0.6, 0, 0)
+    junk["v"]["normal"] = (0, 0, 1)
+    from simple_raytracer_b200.records import concat_records
+    order = rng.permutation(len(real) + len(junk))
+    tris = concat_records(scenes.TRIANGLE, real, junk)[order]
+    sc = _mesh_scene(tris, scenes.translate((0, 0, -3)), scenes.camera_matrix((0, 0, 0.3)), "junk")
+    _check_against_oracle(sc, sky, oracle_lib, "junk triangles")
+
+
+def test_sweep_filter_nan_and_inf_operands(sky, oracle_lib):
+    """A model containing triangles with NaN / inf coordinates, and an AABB that lets every ray in: the filter must
+    pass what it cannot decide, and the exact test then behaves as the reference does."""
+    v, n, f = scenes.noisy_icosphere(2, seed=8)
+    tris = scenes.mesh_triangles(v, f, n)
+    tris["v"]["pos"][5, 1, 0] = np.nan
+    tris["v"]["pos"][17, 2] = (np.inf, 0, 0)
+    tris["v"]["pos"][40, 0, 1] = -np.inf
+    tris["v"]["pos"][41] = 3e38
+    sc = _mesh_scene(tris, scenes.translate((0, 0, -3)), scenes.camera_matrix((0, 0, 0.3)), "nan")
+    sc.shapes["model_bounding_min"][-1], sc.shapes["model_bounding_max"][-1] = (-50, -50, -50), (50, 50, 50)
+    _check_against_oracle(sc, sky, oracle_lib, "nan/inf triangles", min_mesh_pixels=50)
