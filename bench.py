@@ -276,10 +276,20 @@ def main():
                         "peak_gbs": peaks.get("hbm_gbs", 6650.0),
                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback B200_PROFILING.md"},
                 "traffic": None, "counters": counters}
+    # static evidence from the committed ncu capture of the same launch (profiles/): DRAM traffic, and the view that
+    # actually bounds these kernels -- warp-instruction issue (4 schedulers x 1 inst/clk per SM)
     prof = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(prof):
         try:
-            roofline["traffic"] = json.load(open(prof)).get(f"config{args.config}")
+            pj = json.load(open(prof))
+            roofline["traffic"] = pj.get(f"config{args.config}")
+            inst = pj.get(f"config{args.config}_inst_executed")
+            if inst:
+                issue_peak = 148 * 4 * (clocks["sm_mhz"] or 1965.0) * 1e6 / 1e9  # G warp-inst/s
+                issue_ach = inst / (launch_ms * 1e-3) / 1e9
+                roofline["issue"] = {"achieved": issue_ach, "peak": issue_peak, "unit": "G warp-inst/s",
+                                     "frac": issue_ach / issue_peak, "warp_inst_per_launch": inst,
+                                     "source": pj.get(f"config{args.config}_capture")}
         except (OSError, ValueError):
             pass
 
