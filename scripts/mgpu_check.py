@@ -48,7 +48,7 @@ def main():
     # -- tile sharding
     sc = scenes.config3(480, 270, num_samples=2, launches=2)
     tr2 = tracer_for(sc)
-    img_t = D.render_tile_sharded(tr2, sc, rank, world, band_height=8)
+    img_t = D.render_tile_sharded(tr2, sc, rank, world, band_height=2)
     if rank == 0:
         one = tracer_for(sc)
         want_img = D.render_tile_sharded(one, sc, 0, 1)

@@ -61,6 +61,9 @@ def main():
     ap.add_argument("--launches", type=int, default=0, help="override the launch count (0 = the config's)")
     ap.add_argument("--write-ppm", default="")
     ap.add_argument("--mesh-files", action="store_true")
+    ap.add_argument("--band-height", type=int, default=1, help="rows per interleaved band when tile-sharding")
+    ap.add_argument("--sharding", default="", choices=["", "tile", "sample"],
+                    help="override the config's sharding (config 5 = tile, the others = sample)")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -79,11 +82,11 @@ def main():
     tr = tracer.Tracer(sc.width, sc.height, sky, device=local)
     tr.scene_data[:] = sc.scene_data
     tr.update_scene(sc.shapes, sc.triangles, sc.materials)
-    mode = "tile" if args.config == 5 else "sample"
+    mode = args.sharding or ("tile" if args.config == 5 else "sample")
 
     def run():
         if mode == "tile":
-            return D.render_tile_sharded(tr, sc, rank, world, band_height=8, total_launches=launches)
+            return D.render_tile_sharded(tr, sc, rank, world, band_height=args.band_height, total_launches=launches)
         return D.render_sample_sharded(tr, sc, rank, world, total_launches=launches)
 
     def sync():
@@ -93,7 +96,7 @@ def main():
 
     # warm-up on one launch, then the timed full run
     if mode == "tile":
-        D.render_tile_sharded(tr, sc, rank, world, band_height=8, total_launches=1)
+        D.render_tile_sharded(tr, sc, rank, world, band_height=args.band_height, total_launches=1)
     else:
         D.render_sample_sharded(tr, sc, rank, world, total_launches=world)
     sync()
@@ -104,8 +107,10 @@ def main():
     dt = time.perf_counter() - t0
     kernel_ms, n_launch = tr.render_time_ms()
     tmax = torch.tensor([dt, kernel_ms], dtype=torch.float64, device="cuda")
+    tmin = tmax.clone()
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
     # counted work of one launch (rank 0, full frame) for the flop figure
     if rank == 0:
         tr.set_row_bands(1, 0, 1)
@@ -118,6 +123,7 @@ def main():
         out = {"config": args.config, "name": sc.name, "n_gpus": world, "sharding": mode if world > 1 else "none",
                "resolution": f"{sc.width}x{sc.height}", "spp": sc.num_samples * launches, "num_bounces": sc.num_bounces,
                "triangles": int(len(sc.triangles)), "seconds": secs, "max_rank_kernel_ms": float(tmax[1].item()),
+               "min_rank_kernel_ms": float(tmin[1].item()), "band_height": args.band_height if mode == "tile" else None,
                "Msamples_per_s": samples / secs / 1e6, "algorithmic_tflops": flops / secs / 1e12,
                "fp32_peak_measured_tflops": peak, "pct_of_fp32_peak": 100.0 * flops / secs / 1e12 / (peak * world),
                "Gtests_per_s": counters["tri_tests"] * launches / secs / 1e9, "mesh_files": bool(args.mesh_files),
