@@ -371,7 +371,7 @@ __device__ __forceinline__ void scatter(const DevScene &sc, int material, vec3 p
 #define SRT_MIN_BLOCKS 4
 #endif
 #ifndef SRT_MIN_BLOCKS_ANALYTIC
-#define SRT_MIN_BLOCKS_ANALYTIC 6
+#define SRT_MIN_BLOCKS_ANALYTIC 8
 #endif
 constexpr int RENDER_THREADS = SRT_RENDER_THREADS;
 
