@@ -372,3 +372,19 @@ def test_sweep_filter_nan_and_inf_operands(sky, oracle_lib):
     sc = _mesh_scene(tris, scenes.translate((0, 0, -3)), scenes.camera_matrix((0, 0, 0.3)), "nan")
     sc.shapes["model_bounding_min"][-1], sc.shapes["model_bounding_max"][-1] = (-50, -50, -50), (50, 50, 50)
     _check_against_oracle(sc, sky, oracle_lib, "nan/inf triangles", min_mesh_pixels=50)
+
+
+@pytest.mark.skipif(not __import__("oracle").ref_available(), reason="oracle/_ref library not present")
+@pytest.mark.parametrize("cfg,launches,ns", [(1, 1, 1), (2, 2, 4), (3, 1, 1)])
+def test_full_baseline_size_against_the_reference_kernel(sky, oracle_lib, cfg, launches, ns):
+    """BASELINE.json's own sizes (800x600, 1920x1080) against render.cl itself (oracle/_ref on the host cores):
+    every float of the full-frame canvas and every byte of the resolved image."""
+    sc = scenes.CONFIGS[cfg]()
+    tr = make_tracer(sc, sky)
+    got = cuda_canvas(tr, sc, launches, num_samples=ns)
+    ref = None
+    for k in range(launches):
+        ref, _ = oracle_lib.render(sc.render_data(k, num_samples=ns), sc.scene_data, sc.shapes, sc.triangles,
+                                   sc.materials, sky, ref, impl="ref")
+    assert_bit_equal(ref, got, f"C{cfg} full size vs render.cl")
+    assert np.array_equal(oracle_lib.average(launches, ref, impl="ref"), tr.resolve(launches))

@@ -109,3 +109,38 @@ def test_contraction_sensitivity_stays_within_the_stated_tolerances(oracle_lib, 
     a, b = oracle.average(6, ref, impl="ref").astype(float), oracle.average(6, con, impl="contract").astype(float)
     rmse = np.sqrt(np.mean((a - b) ** 2)) / 255.0
     assert rmse <= 1.0 / 255.0, rmse
+
+
+def test_ref_library_was_built_from_the_reference_file_as_it_lies():
+    """oracle/_ref/render.cl.sha256 (written by the Makefile next to the library) names the file that was compiled;
+    where the reference is present it must be that file, byte for byte, and the rewrite must touch nothing but
+    vector literals."""
+    import hashlib
+    import os
+    import re
+    import subprocess
+    here = os.path.dirname(os.path.abspath(oracle.__file__))
+    sha_file = os.path.join(here, "_ref", "render.cl.sha256")
+    if not os.path.exists(oracle.REFERENCE_KERNEL):
+        pytest.skip("reference source not present (GPU box): the prebuilt library is used")
+    oracle.build_ref()
+    src = open(oracle.REFERENCE_KERNEL, "rb").read()
+    assert open(sha_file).read().strip() == hashlib.sha256(src).hexdigest()
+    out = subprocess.run(["python3", os.path.join(here, "ref_build", "rewrite_cl.py"), oracle.REFERENCE_KERNEL],
+                         capture_output=True, text=True, check=True).stdout
+    body = out.split("\n", 1)[1]  # drop the #line directive
+    # undo the rewrite, T(T_lit{ ... }) -> (T)( ... ), and compare modulo white space: nothing else may differ
+    strip = lambda t: re.sub(r"\s+", "", t)  # noqa: E731
+    assert "})" not in strip(src.decode())
+    undone = strip(re.sub(r"\b(float2|float3|float4|uchar4)\(\1_lit\{", r"(\1)(", body)).replace("})", ")")
+    assert undone == strip(src.decode())
+
+
+@pytest.mark.parametrize("seed", range(100, 124))
+def test_oracle_equals_reference_kernel_on_more_random_scenes(oracle_lib, small_sky, seed):
+    sc = random_scene(seed, width=48, height=32, n_spheres=1 + seed % 6, n_planes=seed % 4, n_boxes=seed % 3,
+                      mesh_tris=(0, 7, 33, 150)[seed % 4])
+    rd = sc.render_data(seed, num_samples=2, num_bounces=1 + seed % 12)
+    ref, _ = oracle.render(rd, sc.scene_data, sc.shapes, sc.triangles, sc.materials, small_sky, impl="ref")
+    got, _ = oracle.render(rd, sc.scene_data, sc.shapes, sc.triangles, sc.materials, small_sky)
+    assert_bit_equal(ref, got, f"seed {seed}")
