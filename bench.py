@@ -6,7 +6,7 @@
 
 Workload at N = 1: BASELINE config[1] -- four-sphere material scene + sky box, 1920x1080,
 16 launches x num_samples 4 = 64 spp, 10 bounces.  One "step" = one full pass of that workload:
-clear canvas, 16 `render` launches, one `average`.  At N > 1 (torchrun, one rank per GPU) every rank
+clear canvas, 16 `render` launches (submitted as one batch, srt_render_batch), one `average`.  At N > 1 (torchrun, one rank per GPU) every rank
 renders its own 16 launches with distinct time seeds (sample sharding, weak scaling), the float
 canvases are sum-reduced to rank 0 over NCCL, and rank 0 runs `average` with 16*N steps.
 
@@ -179,8 +179,7 @@ def main():
 
     def device_step():
         tr.clear_canvas()
-        for rd in my_rds:
-            tr.accumulate(rd)
+        tr.accumulate_batch(my_rds)  # the step's 16 launches, one persistent kernel (srt_render_batch)
         if world > 1:
             srt_dist.reduce_canvas(tr, dst=0)
         if rank == 0:
@@ -305,7 +304,7 @@ def main():
         "config": dict(workload, parallelism=f"sample-sharded x{world}" if world > 1 else "single GPU",
                        l2="flushed between timed steps (256 MiB memset, outside the event pairs)",
                        timing="CUDA events per step on the launching stream, summed; max over ranks"),
-        "clocks": clocks, "gpu_launches": args.steps * (2 * L + 1),  # per step: L x (render + accumulate) + average
+        "clocks": clocks, "gpu_launches": args.steps * 3,  # per step: render (16 launches batched) + accumulate + average
         "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "api": "Tracer.update_scene + clear_canvas + 16 x Tracer.render(ticks, host_output) per step, wall clock"},
         "roofline": roofline, "cpu_baseline": cpu_baseline,

@@ -118,6 +118,16 @@ int srt_clear(srt_tracer *t);
  * canvas[id] += mean over num_samples paths (render.cl:483-523).  Asynchronous. */
 int srt_render(srt_tracer *t, const srt_render_data *rd);
 
+/* n consecutive srt_render calls in one: canvas += mean(launch 0), += mean(launch 1), ... -- the same additions in
+ * the same order, so the canvas is bit-identical to n separate calls.  Runs of launches that differ only in `time`
+ * (progressive accumulation with a fixed camera, src/main.cpp:283-290) are executed by ONE persistent kernel over
+ * the combined item space, which removes the ragged end of every launch but the last; anything else falls back to
+ * one kernel per launch.  No reference counterpart (the reference renders one launch per displayed frame). */
+int srt_render_batch(srt_tracer *t, const srt_render_data *rds, size_t n);
+/* Capacity hint (like std::vector::reserve): allocate now the per-sample scratch a batch of n launches shaped like
+ * *rd will need, so that the first srt_render_batch does not pay for the allocation. */
+int srt_reserve_batch(srt_tracer *t, const srt_render_data *rd, size_t n);
+
 /* Replaces the `average` launch + blocking read-back of Tracer::render, tracer.cpp:110-115:
  * argb_out receives width*height*4 bytes in A,R,G,B order (render.cl:525-535).  Synchronises. */
 int srt_resolve(srt_tracer *t, uint32_t num_steps, uint8_t *argb_out);
@@ -147,7 +157,8 @@ int srt_render_counted(srt_tracer *t, const srt_render_data *rd, srt_counters *c
 int srt_debug_math(srt_tracer *t, int op, const float *x, const float *y, float *out, size_t n);
 /* FP32 FMA-chain micro-benchmark on the handle's device: achieved TFLOP/s. */
 int srt_measure_fp32_peak(srt_tracer *t, double *tflops, double *sm_clock_mhz_est);
-/* Mean duration in ms of the render launches since the last call (CUDA events on the handle's stream). */
+/* Total duration in ms of the render launches since the last call (CUDA events on the handle's stream) and how many
+ * reference launches they covered (a batch counts each of its launches). */
 int srt_render_time_ms(srt_tracer *t, double *total_ms, uint64_t *launches);
 
 int srt_destroy(srt_tracer *t);

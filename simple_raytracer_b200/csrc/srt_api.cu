@@ -88,7 +88,8 @@ struct srt_tracer {
 	int band_h = 1, band_i = 0, band_n = 1;
 	int render_grid[2][3] = {{0, 0, 0}, {0, 0, 0}};  // [counted][mode]
 
-	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing;  // render launches since last query
+	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing;  // kernel launches since last query
+	uint64_t timed_launches = 0;                               // reference launches they cover (batches count each)
 	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> event_pool;
 };
 
@@ -158,7 +159,8 @@ int make_params(srt_tracer *t, const srt_render_data *rd, srt::RenderParams &p) 
 	p.fov_scale = rd->fov_scale;
 	p.show_normals = rd->show_normals ? 1 : 0;
 	memcpy(p.c2w, rd->camera_to_world, sizeof p.c2w);
-	p.time = rd->time;
+	p.num_launches = 1;
+	p.times[0] = rd->time;
 	p.inv_ns = (rd->num_samples & (rd->num_samples - 1)) == 0 ? 1.0f / (float)rd->num_samples : 0.0f;
 	p.band_h = t->band_h;
 	p.band_i = t->band_i;
@@ -173,7 +175,8 @@ int make_params(srt_tracer *t, const srt_render_data *rd, srt::RenderParams &p) 
 	p.total_pixels = (unsigned int)rows * (unsigned int)rd->width;
 	if ((unsigned long long)p.total_pixels * (unsigned long long)rd->num_samples > 0xfffffff0ull)
 		return fail(t, SRT_ERR_INVALID, "width*height*num_samples exceeds 2^32 work items per launch");
-	p.total_items = p.total_pixels * (unsigned int)rd->num_samples;
+	p.items_per_launch = p.total_pixels * (unsigned int)rd->num_samples;
+	p.total_items = p.items_per_launch;
 	return SRT_OK;
 }
 
@@ -207,9 +210,18 @@ int launch_render_impl(srt_tracer *t, const srt::RenderParams &p) {
 	if (t->timing.size() >= 4096) {  // nobody is reading the timings: recycle
 		for (auto &e : t->timing) t->event_pool.push_back(e);
 		t->timing.clear();
+		t->timed_launches = 0;
 	}
 	t->timing.push_back(ev);
+	t->timed_launches += (uint64_t)p.num_launches;
 	return SRT_OK;
+}
+
+template <bool COUNT>
+int launch_params(srt_tracer *t, const srt::RenderParams &p) {
+	if (!t->has_models) return launch_render_impl<COUNT, srt::MODE_ANALYTIC>(t, p);
+	if (!t->has_big_models) return launch_render_impl<COUNT, srt::MODE_SMALL_MODELS>(t, p);
+	return launch_render_impl<COUNT, srt::MODE_BIG_MODELS>(t, p);
 }
 
 template <bool COUNT>
@@ -217,9 +229,14 @@ int launch_render(srt_tracer *t, const srt_render_data *rd) {
 	srt::RenderParams p{};
 	if (int rc = make_params(t, rd, p)) return rc;
 	if (p.num_bounces == 0 || p.total_items == 0) return SRT_OK;  // render.cl:403: zero bounces add zero radiance
-	if (!t->has_models) return launch_render_impl<COUNT, srt::MODE_ANALYTIC>(t, p);
-	if (!t->has_big_models) return launch_render_impl<COUNT, srt::MODE_SMALL_MODELS>(t, p);
-	return launch_render_impl<COUNT, srt::MODE_BIG_MODELS>(t, p);
+	return launch_params<COUNT>(t, p);
+}
+
+// true when two launches differ in nothing the kernel reads except `time` (`tick` is unused, render.cl:91)
+bool same_but_time(const srt_render_data &a, const srt_render_data &b) {
+	return a.width == b.width && a.height == b.height && a.num_samples == b.num_samples && a.num_bounces == b.num_bounces &&
+	       memcmp(&a.aspect_ratio, &b.aspect_ratio, 4) == 0 && memcmp(&a.fov_scale, &b.fov_scale, 4) == 0 &&
+	       (a.show_normals != 0) == (b.show_normals != 0) && memcmp(a.camera_to_world, b.camera_to_world, 64) == 0;
 }
 
 }  // namespace
@@ -407,6 +424,45 @@ int srt_clear(srt_tracer *t) {
 int srt_render(srt_tracer *t, const srt_render_data *rd) {
 	SRT_BIND(t);
 	return launch_render<false>(t, rd);
+}
+
+// launches of `p`'s shape one kernel may cover: MAX_BATCH, a 4 GiB budget of per-sample scratch, 2^32 work items
+static size_t batch_cap(const srt::RenderParams &p) {
+	const size_t scratch_budget = (size_t)4 << 30;
+	const size_t fit = std::max<size_t>(1, scratch_budget / ((size_t)p.items_per_launch * sizeof(float4)));
+	return std::min<size_t>({(size_t)srt::MAX_BATCH, fit, (size_t)(0xfffffff0ull / p.items_per_launch)});
+}
+
+int srt_reserve_batch(srt_tracer *t, const srt_render_data *rd, size_t n) {
+	SRT_BIND(t);
+	srt::RenderParams p{};
+	if (int rc = make_params(t, rd, p)) return rc;
+	if (p.total_items == 0 || n == 0) return SRT_OK;
+	SRT_CUDA(t, t->scratch.reserve((size_t)p.items_per_launch * std::min(n, batch_cap(p))));
+	return SRT_OK;
+}
+
+int srt_render_batch(srt_tracer *t, const srt_render_data *rds, size_t n) {
+	SRT_BIND(t);
+	if (n && !rds) return fail(t, SRT_ERR_INVALID, "render data is null");
+	size_t i = 0;
+	while (i < n) {
+		srt::RenderParams p{};
+		if (int rc = make_params(t, &rds[i], p)) return rc;
+		size_t run = 1;
+		if (p.num_bounces > 0 && p.total_items > 0) {
+			const size_t cap = batch_cap(p);
+			while (i + run < n && run < cap && same_but_time(rds[i], rds[i + run])) {
+				p.times[run] = rds[i + run].time;
+				++run;
+			}
+			p.num_launches = (int)run;
+			p.total_items = p.items_per_launch * (unsigned int)run;
+			if (int rc = launch_params<false>(t, p)) return rc;
+		}
+		i += run;
+	}
+	return SRT_OK;
 }
 
 int srt_render_counted(srt_tracer *t, const srt_render_data *rd, srt_counters *counters) {
@@ -613,8 +669,9 @@ int srt_render_time_ms(srt_tracer *t, double *total_ms, uint64_t *launches) {
 		t->event_pool.push_back(e);
 	}
 	if (total_ms) *total_ms = sum;
-	if (launches) *launches = t->timing.size();
+	if (launches) *launches = t->timed_launches;
 	t->timing.clear();
+	t->timed_launches = 0;
 	return SRT_OK;
 }
 

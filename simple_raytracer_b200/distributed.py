@@ -38,8 +38,7 @@ def render_sample_sharded(renderer, scene, rank, world, total_launches=None, dst
     """Sample-sharded accumulation.  Returns the ARGB8 image on rank `dst` (None elsewhere)."""
     total = scene.launches if total_launches is None else total_launches
     renderer.clear_canvas()
-    for k in launch_schedule(total, rank, world):
-        renderer.accumulate(scene.render_data(k))
+    _accumulate_all(renderer, [scene.render_data(k) for k in launch_schedule(total, rank, world)])
     if world > 1:
         (reduce_fn or reduce_canvas)(renderer, dst)
     if rank == dst:
@@ -57,12 +56,21 @@ def render_tile_sharded(renderer, scene, rank, world, band_height=1, total_launc
     total = scene.launches if total_launches is None else total_launches
     renderer.set_row_bands(band_height, rank, world)
     renderer.clear_canvas()
-    for k in range(total):
-        renderer.accumulate(scene.render_data(k))
+    _accumulate_all(renderer, [scene.render_data(k) for k in range(total)])
     renderer.resolve_device(total)
     if world > 1:
         return (gather_fn or gather_output)(renderer, rank, dst)
     return renderer.read_output()
+
+
+def _accumulate_all(renderer, render_datas):
+    """All launches of a rank, batched into shared persistent kernels where the renderer can (srt_render_batch)."""
+    if hasattr(renderer, "accumulate_batch"):
+        if render_datas:
+            renderer.accumulate_batch(render_datas)
+    else:
+        for rd in render_datas:
+            renderer.accumulate(rd)
 
 
 def canvas_tensor(renderer):

@@ -42,6 +42,8 @@ def load_library():
         "srt_upload_scene": [vp, vp, sz, vp, sz, vp, sz, vp],
         "srt_clear": [vp],
         "srt_render": [vp, vp],
+        "srt_render_batch": [vp, vp, sz],
+        "srt_reserve_batch": [vp, vp, sz],
         "srt_resolve": [vp, u32, vp],
         "srt_render_frame": [vp, vp, u32, vp],
         "srt_set_row_bands": [vp, i32, i32, i32],
@@ -134,6 +136,20 @@ class Tracer:
         """The `render` kernel launch alone (asynchronous): canvas += mean of num_samples paths."""
         rd = self.options if render_data is None else np.ascontiguousarray(render_data, RENDER_DATA)
         self._check(self._lib.srt_render(self._h, _p(rd)))
+
+    def accumulate_batch(self, render_datas):
+        """srt_render_batch: the launches of `render_datas` (a sequence of 1-element RenderData records or one
+        record array) in order; runs that differ only in `time` share one persistent kernel."""
+        from .records import concat_records
+        if isinstance(render_datas, np.ndarray) and render_datas.dtype == RENDER_DATA:
+            rds = np.ascontiguousarray(render_datas).reshape(-1)
+        else:
+            rds = concat_records(RENDER_DATA, *render_datas)
+        self._check(self._lib.srt_render_batch(self._h, _p(rds), len(rds)))
+
+    def reserve_batch(self, render_data, n):
+        """srt_reserve_batch: allocate the scratch of an n-launch batch ahead of time."""
+        self._check(self._lib.srt_reserve_batch(self._h, _p(np.ascontiguousarray(render_data, RENDER_DATA)), int(n)))
 
     def accumulate_counted(self, render_data=None, counters=None):
         rd = self.options if render_data is None else np.ascontiguousarray(render_data, RENDER_DATA)

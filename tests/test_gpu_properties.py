@@ -388,3 +388,40 @@ def test_full_baseline_size_against_the_reference_kernel(sky, oracle_lib, cfg, l
                                    sc.materials, sky, ref, impl="ref")
     assert_bit_equal(ref, got, f"C{cfg} full size vs render.cl")
     assert np.array_equal(oracle_lib.average(launches, ref, impl="ref"), tr.resolve(launches))
+
+
+@pytest.mark.parametrize("cfg,w,h,ns,n", [(1, 160, 120, 2, 5), (2, 240, 136, 4, 19), (3, 120, 68, 3, 4), (5, 48, 27, 1, 3)])
+def test_batched_launches_equal_separate_launches(sky, cfg, w, h, ns, n):
+    """srt_render_batch: n launches through one persistent kernel (item space launch x pixel x sample) leave the same
+    canvas, bit for bit, as n srt_render calls -- also beyond MAX_BATCH (19 > 16), under row bands, and when the
+    batch mixes cameras / sample counts so that it has to be split into runs."""
+    sc = scenes.CONFIGS[cfg](w, h)
+    tr = make_tracer(sc, sky)
+    rds = [sc.render_data(k, num_samples=ns) for k in range(n)]
+    want = cuda_canvas(tr, sc, n, num_samples=ns)
+    tr.clear_canvas()
+    tr.accumulate_batch(rds)
+    assert_bit_equal(want, tr.read_canvas(), f"C{cfg} batch of {n}")
+    # row bands
+    tr.set_row_bands(2, 1, 3)
+    tr.clear_canvas()
+    for rd in rds:
+        tr.accumulate(rd)
+    part = tr.read_canvas()
+    tr.clear_canvas()
+    tr.accumulate_batch(rds)
+    assert_bit_equal(part, tr.read_canvas(), f"C{cfg} batch under row bands")
+    tr.set_row_bands(1, 0, 1)
+    # a batch that has to be split: camera moved after two launches, sample count changed for the last one
+    mixed = [sc.render_data(k, num_samples=ns) for k in range(min(n, 4))]
+    mixed[2]["camera_to_world"][0, 3, 0] += 0.25
+    mixed[-1]["num_samples"] = ns + 1
+    tr.clear_canvas()
+    for rd in mixed:
+        tr.accumulate(rd)
+    want = tr.read_canvas()
+    tr.clear_canvas()
+    tr.accumulate_batch(mixed)
+    assert_bit_equal(want, tr.read_canvas(), f"C{cfg} mixed batch")
+    ms, launches = tr.render_time_ms()
+    assert launches > 0 and ms > 0
