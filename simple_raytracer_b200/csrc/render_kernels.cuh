@@ -16,6 +16,24 @@
 
 #include "device_math.cuh"
 
+// Developer build with device-side invariant checks (compute-sanitizer is not available on the GPU pool):
+// scripts/build_variant.sh checks "-DSRT_DEBUG_CHECKS=1", then run the GPU tests with SRT_LIB pointing at it.
+#ifndef SRT_DEBUG_CHECKS
+#define SRT_DEBUG_CHECKS 0
+#endif
+#if SRT_DEBUG_CHECKS
+#include <cstdio>
+#define SRT_ASSERT(cond)                                                       \
+	do {                                                                       \
+		if (!(cond)) {                                                         \
+			printf("SRT_ASSERT failed: %s (line %d)\n", #cond, __LINE__);      \
+			__trap();                                                          \
+		}                                                                      \
+	} while (0)
+#else
+#define SRT_ASSERT(cond) ((void)0)
+#endif
+
 namespace srt {
 
 enum { SHAPE_SPHERE = 0, SHAPE_PLANE = 1, SHAPE_MODEL = 2 };
@@ -471,6 +489,7 @@ __device__ __forceinline__ void triangle_phase(const DevScene &sc, int n, int tr
 	auto issue = [&](int t) {
 		const int st = t % TILE_STAGES;
 		const uint32_t bytes = ((uint32_t)min(TILE_TRIS, n - t * TILE_TRIS) * FLT_BYTES + 15u) & ~15u;  // the array is padded
+		SRT_ASSERT(bytes > 0 && bytes <= (uint32_t)TILE_BYTES && ((size_t)(src + (size_t)t * TILE_BYTES) & 15) == 0);
 		bulk_load_tile(wsmem_s + st * TILE_BYTES, src + (size_t)t * TILE_BYTES, bytes, bars_s + st * 8);
 	};
 	if (lane == 0)
@@ -579,6 +598,7 @@ __device__ __forceinline__ void triangle_phase(const DevScene &sc, int n, int tr
 					uint32_t c = cand[q];
 					const uint32_t base = ((uint32_t)lane << 27) | (uint32_t)(t * TILE_TRIS + q * 32);
 					while (c && rank < room) {
+						SRT_ASSERT(rank >= 0 && pair_count + rank < PAIR_SLOTS && t * TILE_TRIS + q * 32 + (__ffs(c) - 1) < n);
 						if (SRT_PREFETCH_EXACT) {
 							const float4 *pf = exact + 3 * (size_t)(t * TILE_TRIS + q * 32 + (__ffs(c) - 1));
 							asm volatile("prefetch.global.L1 [%0];" ::"l"(pf));
@@ -599,6 +619,7 @@ __device__ __forceinline__ void triangle_phase(const DevScene &sc, int n, int tr
 				if (lane < m) {
 					const uint32_t pr = pairs[(pair_head + lane) & (PAIR_SLOTS - 1)];
 					const int r = pr >> 27, j = pr & (MAX_SWEEP_TRIS - 1);
+					SRT_ASSERT(j >= 0 && j < n && ((ray_mask >> r) & 1u));
 					exact_pair(__ldg(exact + 3 * (size_t)j), __ldg(exact + 3 * (size_t)j + 1), __ldg(exact + 3 * (size_t)j + 2),
 					           rays[3 * r + 2], rays[3 * r], best + r, j);
 				}
@@ -609,9 +630,11 @@ __device__ __forceinline__ void triangle_phase(const DevScene &sc, int n, int tr
 			if (total <= room) break;
 		}
 	}
+	SRT_ASSERT(pair_count == 0);
 	if (active) {
 		const unsigned long long k = best[lane];
 		const unsigned tri1 = (unsigned)k;
+		SRT_ASSERT(tri1 <= (unsigned)n && (k >> 32) <= (unsigned long long)__float_as_uint(hit.t));
 		if (tri1) {
 			hit.t = __uint_as_float((unsigned)(k >> 32));
 			hit.shape = shape;
@@ -625,6 +648,7 @@ __device__ __forceinline__ void triangle_phase(const DevScene &sc, int n, int tr
 __device__ __forceinline__ void start_path(const RenderParams &p, unsigned int item, uint32_t &seed, vec3 &o, vec3 &d) {
 	const unsigned int launch = p.num_launches > 1 ? item / p.items_per_launch : 0u;
 	const unsigned int in_launch = item - launch * p.items_per_launch;
+	SRT_ASSERT(launch < (unsigned)p.num_launches && launch < (unsigned)MAX_BATCH && item < p.total_items);
 	const unsigned int lp = in_launch / (unsigned)p.num_samples;  // local pixel
 	const unsigned int sample = in_launch - lp * (unsigned)p.num_samples;
 	const int row = (int)(lp / (unsigned)p.width);
