@@ -158,9 +158,6 @@ struct TriFlt {
 #ifndef SRT_RAYS_PER_ITER
 #define SRT_RAYS_PER_ITER 2
 #endif
-#ifndef SRT_PREFETCH_EXACT
-#define SRT_PREFETCH_EXACT 0
-#endif
 // With SRT_SWEEP_RMAX the margin is formed once per triangle and tile from the LARGEST R among the parked rays
 // (r.b.y then already holds M = g * Rmax + 2e-6): a larger margin only lets more triangles through.
 __device__ __forceinline__ bool tri_filter_sweep(const TriFlt &r, const float4 rd, const float4 rc) {
@@ -599,11 +596,6 @@ __device__ __forceinline__ void triangle_phase(const DevScene &sc, int n, int tr
 					const uint32_t base = ((uint32_t)lane << 27) | (uint32_t)(t * TILE_TRIS + q * 32);
 					while (c && rank < room) {
 						SRT_ASSERT(rank >= 0 && pair_count + rank < PAIR_SLOTS && t * TILE_TRIS + q * 32 + (__ffs(c) - 1) < n);
-						if (SRT_PREFETCH_EXACT) {
-							const float4 *pf = exact + 3 * (size_t)(t * TILE_TRIS + q * 32 + (__ffs(c) - 1));
-							asm volatile("prefetch.global.L1 [%0];" ::"l"(pf));
-							asm volatile("prefetch.global.L1 [%0];" ::"l"(pf + 2));
-						}
 						pairs[(pair_head + pair_count + rank) & (PAIR_SLOTS - 1)] = base + (__ffs(c) - 1);
 						c &= c - 1;
 						++rank;
