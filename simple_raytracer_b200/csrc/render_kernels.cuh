@@ -144,30 +144,40 @@ __device__ __forceinline__ void tri_exact(const float4 v0, const float4 e1, cons
 // which covers both error terms (the det term three times over, so that a wrong sign of a near-zero det is
 // harmless too).  A triangle is dropped only when the reference's u test is certain to fail; NaNs compare false
 // and survive; every survivor runs tri_exact on the reference operands.
-//   record (40 B): a = {n'.x, n'.y}  b = {n'.z, g}  c = {e2.x, e2.y}  e = {e2.z, m.x}  f = {m.y, m.z}
-//   ray: rd = {d.xyz, R}  rc = {(o x d).xyz, -}
+// det and t = d . m are both dot products with d, so they are evaluated TOGETHER as one chain of packed FP32x2
+// operations (FMUL2, FFMA2, FFMA2: __fmul2_rn / __ffma2_rn, new on sm_100; each half is rounded exactly like the
+// scalar instruction, so nothing changes numerically): 10 instructions per pair instead of 13, and the sweep is
+// bound by instruction issue, not by the FMA pipe.  The record and the ray's shared-memory image are laid out for
+// that: n' and m interleaved, d stored twice.
+//   record (40 B): a = {n'.x, m.x}  b = {n'.y, m.y}  c = {n'.z, m.z}  e = {e2.x, e2.y}  f = {e2.z, g}
+//   ray (48 B): r0 = {d.x, d.x, d.y, d.y}  r1 = {d.z, d.z, c.x, c.y}  r2 = {c.z, o.x, o.y, o.z},  c = o x d
 struct TriFlt {
 	float2 a, b, c, e, f;
 };
-#ifndef SRT_SWEEP_RMAX
-#define SRT_SWEEP_RMAX 1
-#endif
 #ifndef SRT_MARGIN_SCALE  // developer mutation test only: 0 removes the error margins of the sweep filter
 #define SRT_MARGIN_SCALE 1.0f
 #endif
 #ifndef SRT_RAYS_PER_ITER
 #define SRT_RAYS_PER_ITER 2
 #endif
-// With SRT_SWEEP_RMAX the margin is formed once per triangle and tile from the LARGEST R among the parked rays
-// (r.b.y then already holds M = g * Rmax + 2e-6): a larger margin only lets more triangles through.
-__device__ __forceinline__ bool tri_filter_sweep(const TriFlt &r, const float4 rd, const float4 rc) {
-	float det = fma_(rd.z, r.b.x, fma_(rd.y, r.a.y, rd.x * r.a.x));
-	float t = fma_(rd.z, r.f.y, fma_(rd.y, r.f.x, rd.x * r.e.y));
-	float su = fma_(r.e.x, rc.z, fma_(r.c.y, rc.y, fma_(r.c.x, rc.x, -t)));
-	float x = __int_as_float(__float_as_int(su) ^ (__float_as_int(det) & 0x80000000));
-	float m = SRT_SWEEP_RMAX ? r.b.y : fma_(r.b.y, rd.w, 2e-6f * SRT_MARGIN_SCALE);
-	float lim = fma_(fabsf(det), 1.000002f, m);
-	return !(x > lim || x < -m);
+// The margin is formed once per triangle and tile from the LARGEST R among the parked rays (M = g * Rmax + 2e-6):
+// a larger margin only lets more triangles through.
+// m: the margin M of this triangle for the phase (g * Rmax + 2e-6, formed once per tile); cz = r2.x
+__device__ __forceinline__ bool tri_filter_sweep(const TriFlt &r, const float m, const float4 r0, const float4 r1,
+                                                 const float cz) {
+	// {det, t} = d.x {n'.x, m.x} + d.y {n'.y, m.y} + d.z {n'.z, m.z}
+	const float2 dt = __ffma2_rn(make_float2(r1.x, r1.y), r.c,
+	                             __ffma2_rn(make_float2(r0.z, r0.w), r.b, __fmul2_rn(make_float2(r0.x, r0.y), r.a)));
+	const float det = dt.x;
+	const float su = fma_(r.f.x, cz, fma_(r.e.y, r1.w, fma_(r.e.x, r1.z, -dt.y)));
+	// x = su sign(det) in [-M, |det| (1 + 2e-6) + M]  <=>  |su - det k| <= |det| k + M  with k = (1 + 2e-6) / 2: the
+	// interval test as a distance from its centre.  Same decision up to a few u |det| of rounding in the centre and
+	// half-width, which the slack in k and M absorbs.  Three of these four instructions run on the FMA
+	// pipe and one on the half-rate ALU pipe, against one and three for a sign flip and two compares.  A NaN fails
+	// `>` and survives.
+	const float diff = su - det * 0.500001f;
+	const float w = fma_(fabsf(det), 0.500001f, m);
+	return !(fabsf(diff) > w);
 }
 __device__ __forceinline__ void test_triangle(const float4 v0, const float4 e1, const float4 e2, vec3 o, vec3 d,
                                               int shape, int tri, Hit &hit) {
@@ -493,20 +503,19 @@ __device__ __forceinline__ void triangle_phase(const DevScene &sc, int n, int tr
 		for (int t = 0; t < min(ntiles, TILE_STAGES); ++t) issue(t);
 	if (active) {  // per-ray operands: d, R = |o|_1 + K, c = o x d for the filter; o for the exact test
 		const vec3 c = cross(o, d);
-		rays[3 * lane] = make_float4(d.x, d.y, d.z, fabsf(o.x) + fabsf(o.y) + fabsf(o.z) + __ldg(&sc.model_k[shape]));
-		rays[3 * lane + 1] = make_float4(c.x, c.y, c.z, 0.f);
-		rays[3 * lane + 2] = make_float4(o.x, o.y, o.z, 0.f);
+		rays[3 * lane] = make_float4(d.x, d.x, d.y, d.y);
+		rays[3 * lane + 1] = make_float4(d.z, d.z, c.x, c.y);
+		rays[3 * lane + 2] = make_float4(c.z, o.x, o.y, o.z);
 		best[lane] = (unsigned long long)__float_as_uint(hit.t) << 32;
 	}
 	const unsigned ray_mask = __ballot_sync(FULL, active);
 	int pair_head = 0, pair_count = 0;  // warp-uniform
-	float rmax = active ? rays[3 * lane].w : 0.0f;  // NaN (a ray the filter cannot decide) must win the max
-	if (SRT_SWEEP_RMAX) {
+	// R = |o|_1 + K of my ray; its maximum over the parked rays (NaN -- a ray the filter cannot decide -- must win)
+	float rmax = active ? fabsf(o.x) + fabsf(o.y) + fabsf(o.z) + __ldg(&sc.model_k[shape]) : 0.0f;
 #pragma unroll
-		for (int off = 16; off > 0; off >>= 1) {
-			const float other = __shfl_xor_sync(FULL, rmax, off);
-			rmax = (other > rmax || other != other) ? other : rmax;
-		}
+	for (int off = 16; off > 0; off >>= 1) {
+		const float other = __shfl_xor_sync(FULL, rmax, off);
+		rmax = (other > rmax || other != other) ? other : rmax;
 	}
 	__syncwarp();
 
@@ -529,38 +538,42 @@ __device__ __forceinline__ void triangle_phase(const DevScene &sc, int n, int tr
 			for (int q = 0; q < TRIS_PER_LANE; ++q) {
 				const float2 *r = tile + 5 * (q * 32 + lane);  // 40 B stride: conflict-free LDS.64
 				tf[q].a = r[0], tf[q].b = r[1], tf[q].c = r[2], tf[q].e = r[3], tf[q].f = r[4];
-				if (SRT_SWEEP_RMAX) tf[q].b.y = fma_(tf[q].b.y, rmax, 2e-6f * SRT_MARGIN_SCALE);
+				tf[q].f.y = fma_(tf[q].f.y, rmax, 2e-6f * SRT_MARGIN_SCALE);  // g -> M
 			}
 #if SRT_RAYS_PER_ITER == 2
 			// two parked rays per trip: half the loop overhead per ray and eight independent dependency chains
 			unsigned rm = ray_mask;
 			for (; rm & (rm - 1); rm &= rm - 1, rm &= rm - 1) {  // warp-uniform; at least two rays left
 				const int r0 = __ffs(rm) - 1, r1 = __ffs(rm & (rm - 1)) - 1;
-				const float4 rd0 = rays[3 * r0], rc0 = rays[3 * r0 + 1], rd1 = rays[3 * r1], rc1 = rays[3 * r1 + 1];
+				const float4 a0 = rays[3 * r0], a1 = rays[3 * r0 + 1], b0 = rays[3 * r1], b1 = rays[3 * r1 + 1];
+				const float acz = reinterpret_cast<const float *>(rays + 3 * r0 + 2)[0];
+				const float bcz = reinterpret_cast<const float *>(rays + 3 * r1 + 2)[0];
 #pragma unroll
 				for (int q = 0; q < TRIS_PER_LANE; ++q) {
-					const unsigned v0 = __ballot_sync(FULL, tri_filter_sweep(tf[q], rd0, rc0));
-					const unsigned v1 = __ballot_sync(FULL, tri_filter_sweep(tf[q], rd1, rc1));
+					const unsigned v0 = __ballot_sync(FULL, tri_filter_sweep(tf[q], tf[q].f.y, a0, a1, acz));
+					const unsigned v1 = __ballot_sync(FULL, tri_filter_sweep(tf[q], tf[q].f.y, b0, b1, bcz));
 					if (lane == r0) cand[q] = v0;
 					if (lane == r1) cand[q] = v1;
 				}
 			}
 			if (rm) {  // odd one out
 				const int r = __ffs(rm) - 1;
-				const float4 rd4 = rays[3 * r], rc4 = rays[3 * r + 1];
+				const float4 a0 = rays[3 * r], a1 = rays[3 * r + 1];
+				const float acz = reinterpret_cast<const float *>(rays + 3 * r + 2)[0];
 #pragma unroll
 				for (int q = 0; q < TRIS_PER_LANE; ++q) {
-					const unsigned v = __ballot_sync(FULL, tri_filter_sweep(tf[q], rd4, rc4));
+					const unsigned v = __ballot_sync(FULL, tri_filter_sweep(tf[q], tf[q].f.y, a0, a1, acz));
 					if (lane == r) cand[q] = v;
 				}
 			}
 #else
 			for (unsigned rm = ray_mask; rm; rm &= rm - 1) {  // warp-uniform loop over the parked rays
 				const int r = __ffs(rm) - 1;
-				const float4 rd4 = rays[3 * r], rc4 = rays[3 * r + 1];  // broadcast
+				const float4 a0 = rays[3 * r], a1 = rays[3 * r + 1];  // broadcast
+				const float acz = reinterpret_cast<const float *>(rays + 3 * r + 2)[0];
 #pragma unroll
 				for (int q = 0; q < TRIS_PER_LANE; ++q) {
-					const unsigned v = __ballot_sync(FULL, tri_filter_sweep(tf[q], rd4, rc4));
+					const unsigned v = __ballot_sync(FULL, tri_filter_sweep(tf[q], tf[q].f.y, a0, a1, acz));
 					if (lane == r) cand[q] = v;
 				}
 			}
@@ -612,8 +625,9 @@ __device__ __forceinline__ void triangle_phase(const DevScene &sc, int n, int tr
 					const uint32_t pr = pairs[(pair_head + lane) & (PAIR_SLOTS - 1)];
 					const int r = pr >> 27, j = pr & (MAX_SWEEP_TRIS - 1);
 					SRT_ASSERT(j >= 0 && j < n && ((ray_mask >> r) & 1u));
+					const float4 q0 = rays[3 * r], q1 = rays[3 * r + 1], q2 = rays[3 * r + 2];
 					exact_pair(__ldg(exact + 3 * (size_t)j), __ldg(exact + 3 * (size_t)j + 1), __ldg(exact + 3 * (size_t)j + 2),
-					           rays[3 * r + 2], rays[3 * r], best + r, j);
+					           make_float4(q2.y, q2.z, q2.w, 0.f), make_float4(q0.x, q0.z, q1.x, 0.f), best + r, j);
 				}
 				pair_head = (pair_head + m) & (PAIR_SLOTS - 1);
 				pair_count -= m;
@@ -1032,11 +1046,11 @@ prepare_triangles_kernel(const float4 *__restrict__ aos /* 6 float4 per triangle
 	const float n1e1 = fabsf(e1.x) + fabsf(e1.y) + fabsf(e1.z), n1e2 = fabsf(e2.x) + fabsf(e2.y) + fabsf(e2.z);
 	const float n1v0 = fabsf(w[0].x) + fabsf(w[0].y) + fabsf(w[0].z);
 	float2 *r = flt_out + 5 * (size_t)g;
-	r[0] = make_float2(np.x, np.y);
-	r[1] = make_float2(np.z, 48.0f * SRT_MARGIN_SCALE * U * n1e2);
-	r[2] = make_float2(e2.x, e2.y);
-	r[3] = make_float2(e2.z, m.x);
-	r[4] = make_float2(m.y, m.z);
+	r[0] = make_float2(np.x, m.x);
+	r[1] = make_float2(np.y, m.y);
+	r[2] = make_float2(np.z, m.z);
+	r[3] = make_float2(e2.x, e2.y);
+	r[4] = make_float2(e2.z, 48.0f * SRT_MARGIN_SCALE * U * n1e2);
 	const float k = n1v0 + 3.0f * n1e1;  // non-negative (or NaN, which the filter then passes): orders like its bits
 	atomicMax(reinterpret_cast<unsigned int *>(model_k + sp.shape), __float_as_uint(k == k ? k : __int_as_float(0x7f800000)));
 }
