@@ -144,3 +144,33 @@ def test_oracle_equals_reference_kernel_on_more_random_scenes(oracle_lib, small_
     ref, _ = oracle.render(rd, sc.scene_data, sc.shapes, sc.triangles, sc.materials, small_sky, impl="ref")
     got, _ = oracle.render(rd, sc.scene_data, sc.shapes, sc.triangles, sc.materials, small_sky)
     assert_bit_equal(ref, got, f"seed {seed}")
+
+
+def test_reference_kernel_result_does_not_depend_on_the_optimisation_level(small_sky, tmp_path):
+    """The _ref build is meant to be THE IEEE-754 result of render.cl under the documented builtins, not an artefact
+    of g++ -O2: the same source compiled -O0 and -O3 (still -ffp-contract=off) must give the same bits."""
+    import ctypes
+    import os
+    import subprocess
+    if not os.path.exists(oracle.REFERENCE_KERNEL):
+        pytest.skip("reference source not present")
+    here = os.path.dirname(os.path.abspath(oracle.__file__))
+    sc = scenes.config3(64, 36)
+    rd = sc.render_data(3, num_samples=2)
+    want, _ = oracle.render(rd, sc.scene_data, sc.shapes, sc.triangles, sc.materials, small_sky, impl="ref")
+    for opt in ("-O0", "-O3"):
+        so = str(tmp_path / f"ref{opt}.so")
+        define = "-DREF_KERNEL_SOURCE='\"/dev/stdin\"'"
+        cmd = (f"python3 {here}/ref_build/rewrite_cl.py {oracle.REFERENCE_KERNEL} | g++ -std=c++20 {opt} -march=x86-64-v3 "
+               f"-ffp-contract=off -fno-fast-math -fopenmp -fPIC -Wno-narrowing -w -I{here}/ref_build "
+               f"{define} -shared -o {so} {here}/ref_build/ref_driver.cpp -lm")
+        subprocess.check_call(["bash", "-c", cmd])
+        lib = ctypes.CDLL(so)
+        vp, i32 = ctypes.c_void_p, ctypes.c_int
+        lib.ref_render.argtypes = [vp] * 7 + [i32] * 10
+        canvas = np.zeros((36, 64, 4), np.float32)
+        sd = sc.scene_data.copy()
+        p = lambda a: a.ctypes.data_as(vp)  # noqa: E731
+        lib.ref_render(p(rd), p(sd), p(canvas), p(sc.shapes), p(sc.triangles), p(sc.materials), p(small_sky),
+                       small_sky.shape[1], small_sky.shape[0], 0, 0, 64, 36, 1, 0, 1, 0)
+        assert_bit_equal(want, canvas, f"g++ {opt}")
