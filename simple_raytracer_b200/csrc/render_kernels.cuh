@@ -119,7 +119,7 @@ __device__ __forceinline__ void tri_exact(const float4 v0, const float4 e1, cons
 	float det = dot(xyz(e1), h);
 	// det == 0 (render.cl:253) needs no test of its own: then f = +-inf and t below is +-inf or NaN,
 	// which can never satisfy t < hit.t
-	float f = div_(1.0f, det);
+	float f = rcp_(det);
 	vec3 s = o - xyz(v0);
 	float u = f * dot(s, h);
 	if (u < 0.0f || u > 1.0f) return;
@@ -377,7 +377,7 @@ __device__ __forceinline__ void scatter(const DevScene &sc, int material, vec3 p
 	} else {
 		float ki = 2.0f * dot(rough, n);                        // in_dir = reflect(rough, n), :440
 		vec3 in_dir = mk(cfma_(-ki, n.x, rough.x), cfma_(-ki, n.y, rough.y), cfma_(-ki, n.z, rough.z));
-		float mu = front ? div_(1.0f, m1.y) : m1.y;             // :442
+		float mu = front ? rcp_(m1.y) : m1.y;             // :442
 		float cos_theta = min_(1.0f, dot(in_dir, -n));          // :443
 		float sin_theta = sqrt_(cfma_(-cos_theta, cos_theta, 1.0f));
 		bool reflected_t = mu * sin_theta > 1.0f;               // :446
@@ -831,7 +831,7 @@ render_kernel(const __grid_constant__ RenderParams p, const __grid_constant__ De
 				hit.t = __int_as_float(0x7f800000);
 				hit.shape = -1;
 				hit.tri = -1;
-				if (MODELS) inv = mk(div_(1.0f, d.x), div_(1.0f, d.y), div_(1.0f, d.z));
+				if (MODELS) inv = mk(rcp_(d.x), rcp_(d.y), rcp_(d.z));
 				scan_at = 0;
 			}
 			park = scan_shapes<COUNT, PHASES, MODELS>(sc, o, d, inv, scan_at, hit, cnt);
@@ -995,7 +995,7 @@ primary_kernel(const __grid_constant__ RenderParams p, const __grid_constant__ D
 	camera_ray(p, gx, gy, seed, o, d);
 	Counters cnt = {0, 0, 0, 0, 0, 0};
 	Hit hit = {__int_as_float(0x7f800000), -1, -1};
-	vec3 inv = mk(div_(1.0f, d.x), div_(1.0f, d.y), div_(1.0f, d.z));
+	vec3 inv = mk(rcp_(d.x), rcp_(d.y), rcp_(d.z));
 	scan_shapes<false, false>(sc, o, d, inv, 0, hit, cnt);
 	shape_idx[id] = hit.shape;
 	t_out[id] = hit.t;
