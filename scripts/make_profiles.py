@@ -41,6 +41,7 @@ if traffic:
     json.dump(traffic, open(os.path.join(P, "roofline_traffic.json"), "w"), indent=1)
 
 for f in (f"{rnd}_bench.json", f"{rnd}_bench_reference.json", f"{rnd}_bench_launches.csv", f"{rnd}_configs_n1.jsonl",
+          f"{rnd}_bench_n2.json", f"{rnd}_configs_n2.jsonl", f"{rnd}_bench_n4.json", f"{rnd}_configs_n4.jsonl",
           f"{rnd}_bench_n8.json", f"{rnd}_configs_n8.jsonl"):
     if os.path.exists(os.path.join(G, f)):
         shutil.copy(os.path.join(G, f), os.path.join(P, f))

@@ -35,6 +35,14 @@ one = {c["config"]: c for c in cfg}
 rows8 = "".join(f"| C{c['config']} | {c['sharding']} | {c['max_rank_kernel_ms']:.1f} / {c['min_rank_kernel_ms']:.1f} | {c['Msamples_per_s']:.0f} | "
                 f"{c['Msamples_per_s'] / one[c['config']]['Msamples_per_s']:.2f} × | {c['pct_of_fp32_peak']:.1f} % |\n" for c in cfg8)
 shares = open(os.path.join(P, f"{rnd}_bench_launch_shares.txt")).read()
+scal = "| GPUs | bench (config 2, weak) Msamples/s | e2e Msamples/s | config 4 (strong) Msamples/s | config 5 tile-sharded (strong) Msamples/s |\n|---|---|---|---|---|\n"
+scal += f"| 1 | {b['value']:.0f} | {b['e2e']['value']:.0f} | {one[4]['Msamples_per_s']:.0f} | {one[5]['Msamples_per_s']:.1f} |\n"
+for n in (2, 4, 8):
+    bn = L(f"{rnd}_bench_n{n}.json")
+    cn = {(c["config"], c["sharding"]): c for c in (json.loads(l) for l in open(os.path.join(P, f"{rnd}_configs_n{n}.jsonl")))}
+    scal += (f"| {n} | {bn['value']:.0f} ({bn['value'] / b['value']:.2f} ×) | {bn['e2e']['value']:.0f} | "
+             f"{cn[(4, 'sample')]['Msamples_per_s']:.0f} ({cn[(4, 'sample')]['Msamples_per_s'] / one[4]['Msamples_per_s']:.2f} ×) | "
+             f"{cn[(5, 'tile')]['Msamples_per_s']:.1f} ({cn[(5, 'tile')]['Msamples_per_s'] / one[5]['Msamples_per_s']:.2f} ×) |\n")
 sweep3 = seg_share(3, lambda n, act, ops: "VOTE.ANY" in ops and act > 31)
 sweep5 = seg_share(5, lambda n, act, ops: "VOTE.ANY" in ops and act > 31)
 exact3 = seg_share(3, lambda n, act, ops: act > 30 and ("LDG.E.128" in ops or "FSETP.LT.OR" in ops))
@@ -92,7 +100,11 @@ One GPU:
 | config | resolution | spp | triangles | kernel ms | Msamples/s | algorithmic TFLOP/s | % of measured FP32 peak | G ray×tri tests/s |
 |---|---|---|---|---|---|---|---|---|
 {rows}
-Eight GPUs (strong scaling: total work fixed; % of peak is of 8 × the measured single-GPU peak):
+Scaling on one box (`{rnd}_bench_n{{2,4,8}}.json`, `{rnd}_configs_n{{2,4,8}}.jsonl`; every number is the max over ranks of
+device time, plus the collective):
+
+{scal}
+Eight GPUs in detail (strong scaling: total work fixed; % of peak is of 8 × the measured single-GPU peak):
 
 | config | sharding | kernel ms, slowest / fastest rank | Msamples/s | vs the one-GPU table | % of FP32 peak |
 |---|---|---|---|---|---|
@@ -132,7 +144,7 @@ lane occupancy).  Remaining headroom in the sweep: 16 warps/SM (≈ 125 register
 * `{rnd}_bench.json`, `{rnd}_bench_reference.json`, `{rnd}_bench_n8.json` — `bench.py`, both arms on the same box; 8 GPUs.
 * `{rnd}_bench_launches.csv`, `{rnd}_bench_launch_shares.txt` — ncu launch list of `bench.py --steps 2 --warmup 3` and its per-kernel sums.
 * `{rnd}_configs_n1.jsonl`, `{rnd}_configs_n8.jsonl` — all configs on 1 GPU; configs 4, 5 (tile and sample sharded) on 8.
-  `{rnd}_bench_n2.json` — an early 2-GPU bench line (kernel since improved).
+  `{rnd}_bench_n{{2,4}}.json`, `{rnd}_configs_n{{2,4}}.jsonl` — the same on 2 and 4 GPUs.
 * `{rnd}_ncu_c{{2,3,5}}_key_metrics.txt` — metrics of the render kernel from `ncu --set full --clock-control none
   --import-source on` (`scripts/ncu_capture.sh`); `{rnd}_ncu_c{{2,3,5}}_segments.txt` — per-SASS-segment instruction and
   sample shares from the source page (`scripts/ncu_segments.py`).
