@@ -131,7 +131,12 @@ not the ragged end of each launch; batching did.
 (before: `git show 710f4f2:profiles/r1_ncu_c3_key_metrics.txt` etc.)  Steps, each measured on its own: pre-multiplied
 filter operands 97 → 77 instructions per ray-tile; survivors through a pair ring and one dense exact pass; margin
 hoisted per tile; two rays per trip; interval test as a distance from its centre (ALU → FMA pipe); `(det, t)` as one
-packed FP32x2 chain (`FMUL2`/`FFMA2`) 72.5 → 62.5.  An intermediate version with three inlined copies of the exact test
+packed FP32x2 chain (`FMUL2`/`FFMA2`) 72.5 → 62.5.  Packing *everything* (two triangles per FP32x2 operation, tile records
+interleaved in pairs: 52 instructions per ray-tile, 114 registers) was built, passed every test, and ran no faster
+(`{rnd}_ncu_c5_allpacked_experiment.txt`): `issue_active` fell from 75 % to 63 % at the same duration, every FMA-pipe
+cycle landed on the `fmaheavy` sub-pipe (`sm__pipe_fmaheavy_cycles_active` = `sm__pipe_fma_cycles_active`, i.e. `fmalite`
+idle) and `math_pipe_throttle` doubled — packed FP32x2 instructions issue to `fmaheavy` only, so the mix that keeps
+both sub-pipes busy (3 packed + 6 scalar FP instructions per pair) stays.  An intermediate version with three inlined copies of the exact test
 (4 232 SASS instructions instead of 2 936) executed 22 % fewer instructions than "before" and ran 14 % *slower*:
 `stalled_no_instruction` 2.9 per issued instruction, issue_active 49 % — instruction-cache thrashing between warps in
 different phases.  Folding every survivor path into one drain loop fixed it (`stalled_no_instruction` 0.17).  Where
