@@ -146,9 +146,10 @@ __device__ __forceinline__ void tri_exact(const float4 v0, const float4 e1, cons
 // and survive; every survivor runs tri_exact on the reference operands.
 // det and t = d . m are both dot products with d, so they are evaluated TOGETHER as one chain of packed FP32x2
 // operations (FMUL2, FFMA2, FFMA2: __fmul2_rn / __ffma2_rn, new on sm_100; each half is rounded exactly like the
-// scalar instruction, so nothing changes numerically): 10 instructions per pair instead of 13, and the sweep is
-// bound by instruction issue, not by the FMA pipe.  The record and the ray's shared-memory image are laid out for
-// that: n' and m interleaved, d stored twice.
+// scalar instruction, so nothing changes numerically): 10 instructions per pair instead of 13.  Packed instructions
+// issue to the fmaheavy sub-pipe only, so packing more than this (two triangles per operation was tried) idles
+// fmalite and gains nothing.  The record and the ray's shared-memory image are laid out for it: n' and m interleaved,
+// d stored twice.
 //   record (40 B): a = {n'.x, m.x}  b = {n'.y, m.y}  c = {n'.z, m.z}  e = {e2.x, e2.y}  f = {e2.z, g}
 //   ray (48 B): r0 = {d.x, d.x, d.y, d.y}  r1 = {d.z, d.z, c.x, c.y}  r2 = {c.z, o.x, o.y, o.z},  c = o x d
 struct TriFlt {
