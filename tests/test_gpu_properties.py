@@ -425,3 +425,22 @@ def test_batched_launches_equal_separate_launches(sky, cfg, w, h, ns, n):
     assert_bit_equal(want, tr.read_canvas(), f"C{cfg} mixed batch")
     ms, launches = tr.render_time_ms()
     assert launches > 0 and ms > 0
+
+
+@pytest.mark.parametrize("key", ["config1", "config2", "config3", "config4", "config5_480x270"])
+def test_full_size_canvas_digest_of_the_reference_kernel(sky, key):
+    """Full-size canvases and resolved images against SHA-256 digests of what the reference kernel produced for the
+    same seeded scene (tests/golden/fullsize_hashes.json): BASELINE sizes incl. 4K, and the 100 352-triangle mesh."""
+    import hashlib
+    import fullsize_util
+    h = fullsize_util.load()
+    e = h[key]
+    if hashlib.sha256(sky.tobytes()).hexdigest() != h["sky_sha256"]:
+        pytest.skip("procedural sky differs on this platform")
+    sc, same = fullsize_util.scene_for(e)
+    if not same:
+        pytest.skip("scene builder produced different bytes on this platform")
+    tr = make_tracer(sc, sky)
+    canvas = cuda_canvas(tr, sc, e["launches"], num_samples=e["num_samples"])
+    assert fullsize_util.canvas_digest(canvas) == e["canvas_sha256"]
+    assert hashlib.sha256(tr.resolve(e["launches"]).tobytes()).hexdigest() == e["argb_sha256"]
