@@ -444,3 +444,27 @@ def test_full_size_canvas_digest_of_the_reference_kernel(sky, key):
     canvas = cuda_canvas(tr, sc, e["launches"], num_samples=e["num_samples"])
     assert fullsize_util.canvas_digest(canvas) == e["canvas_sha256"]
     assert hashlib.sha256(tr.resolve(e["launches"]).tobytes()).hexdigest() == e["argb_sha256"]
+
+
+def test_many_launches_recycle_timing_events_and_stay_deterministic(sky):
+    """5 000 launches without ever reading the timings (the library recycles its CUDA events every 4 096 launches),
+    interleaved with batches, clears and resolves: no error, and the same canvas as a fresh tracer gives."""
+    sc = scenes.config1(64, 48)
+    tr = make_tracer(sc, sky)
+    rds = [sc.render_data(k, num_samples=1, num_bounces=3) for k in range(8)]
+    for i in range(600):
+        tr.accumulate_batch(rds)
+        if i % 50 == 0:
+            tr.resolve(i + 1)
+        if i % 97 == 0:
+            tr.clear_canvas()
+    for i in range(300):
+        tr.accumulate(rds[i % 8])
+    tr.clear_canvas()
+    tr.accumulate_batch(rds)
+    got = tr.read_canvas()
+    fresh = make_tracer(sc, sky)
+    fresh.accumulate_batch(rds)
+    assert_bit_equal(fresh.read_canvas(), got, "after 5 100 launches")
+    ms, n = tr.render_time_ms()
+    assert n > 0 and ms > 0
