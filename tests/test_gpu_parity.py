@@ -144,3 +144,35 @@ def test_golden_fixture(cfg):
         tr.accumulate(rd[k:k + 1])
     assert_bit_equal(g["canvas"], tr.read_canvas(), f"golden C{cfg} canvas")
     assert np.array_equal(g["argb"], tr.resolve(len(rd)))
+
+
+@needs_ref
+def test_random_launch_parameters_against_the_reference_kernel(ctx, small_sky):
+    """Launch parameters themselves randomised: image size (down to 1x1), sample / bounce counts (0 bounces too), time
+    seeds (0, wrapping products), camera pose, fov, show_normals -- each against render.cl, single launches and a batch."""
+    oracle = ctx["oracle"]
+    rng = np.random.default_rng(2026)
+    times = [0, 1, 2, 1000003, 809679, 0x7fffffff, 0xffffffff, 404838]
+    for trial in range(40):
+        w, h = int(rng.integers(1, 70)), int(rng.integers(1, 50))
+        seed = int(rng.integers(0, 6))
+        sc = random_scene(seed, width=w, height=h, mesh_tris=(0, 9, 70)[trial % 3])
+        sc.camera = scenes.camera_matrix((0.1 * seed, 0.3, 3.0), rng.uniform(-3, 3), rng.uniform(-1.2, 1.2))
+        sc.fov_scale = np.float32(rng.uniform(0.2, 2.5))
+        rds = []
+        for k in range(3):
+            rd = sc.render_data(k, num_samples=int(rng.integers(1, 6)) if k == 0 else None, show_normals=bool(trial % 7 == 0))
+            rd["num_samples"] = rds[0]["num_samples"] if rds else rd["num_samples"]
+            rd["num_bounces"] = int(rng.integers(0, 10)) if k == 0 else rds[0]["num_bounces"]
+            rd["time"] = times[int(rng.integers(len(times)))]
+            rds.append(rd)
+        tr = make_tracer(sc, small_sky)
+        ref = None
+        for rd in rds:
+            tr.accumulate(rd)
+            ref, _ = oracle.render(rd, sc.scene_data, sc.shapes, sc.triangles, sc.materials, small_sky, ref, impl="ref")
+        assert_bit_equal(ref, tr.read_canvas(), f"trial {trial}: {w}x{h}")
+        tr.clear_canvas()
+        tr.accumulate_batch(rds)
+        assert_bit_equal(ref, tr.read_canvas(), f"trial {trial}: {w}x{h} (batch)")
+        tr.close()

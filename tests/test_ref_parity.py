@@ -174,3 +174,27 @@ def test_reference_kernel_result_does_not_depend_on_the_optimisation_level(small
         lib.ref_render(p(rd), p(sd), p(canvas), p(sc.shapes), p(sc.triangles), p(sc.materials), p(small_sky),
                        small_sky.shape[1], small_sky.shape[0], 0, 0, 64, 36, 1, 0, 1, 0)
         assert_bit_equal(want, canvas, f"g++ {opt}")
+
+
+def test_hypothesis_random_launch_parameters_oracle_equals_reference_kernel(oracle_lib, small_sky):
+    """Property test over the launch parameters themselves: image size (down to 1x1), sample and bounce counts, time
+    seeds (incl. 0 and values whose product with 5304 wraps), camera pose, fov, show_normals."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None, derandomize=True)
+    @given(w=st.integers(1, 40), h=st.integers(1, 30), ns=st.integers(1, 5), nb=st.integers(0, 9),
+           time=st.sampled_from([0, 1, 2, 1000003, 809679, 0x7fffffff, 0xffffffff, 404838]),
+           yaw=st.floats(-3.0, 3.0), pitch=st.floats(-1.2, 1.2), fov=st.floats(0.2, 2.5), normals=st.booleans(),
+           seed=st.integers(0, 5))
+    def check(w, h, ns, nb, time, yaw, pitch, fov, normals, seed):
+        sc = random_scene(seed, width=w, height=h, mesh_tris=9 if seed % 2 else 0)
+        sc.camera = scenes.camera_matrix((0.1 * seed, 0.3, 3.0), yaw, pitch)
+        sc.fov_scale = np.float32(fov)
+        rd = sc.render_data(0, num_samples=ns, show_normals=normals)
+        rd["num_bounces"] = nb
+        rd["time"] = time
+        ref, _ = oracle.render(rd, sc.scene_data, sc.shapes, sc.triangles, sc.materials, small_sky, impl="ref")
+        got, _ = oracle.render(rd, sc.scene_data, sc.shapes, sc.triangles, sc.materials, small_sky)
+        assert_bit_equal(ref, got, f"{w}x{h} ns={ns} nb={nb} time={time}")
+
+    check()
