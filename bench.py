@@ -4,20 +4,29 @@
     python bench.py --gpus N --steps K --warmup W          # CUDA arm (this repository)
     python bench.py --impl reference --steps K --warmup W  # CPU arm: the reference algorithm on host cores
 
-Workload at N = 1: BASELINE config[1] -- four-sphere material scene + sky box, 1920x1080,
-16 launches x num_samples 4 = 64 spp, 10 bounces.  One "step" = one full pass of that workload:
-clear canvas, 16 `render` launches (submitted as one batch, srt_render_batch), one `average`.  At N > 1 (torchrun, one rank per GPU) every rank
-renders its own 16 launches with distinct time seeds (sample sharding, weak scaling), the float
-canvases are sum-reduced to rank 0 over NCCL, and rank 0 runs `average` with 16*N steps.
+Headline workload (`value`, `e2e`, `roofline`, `cpu_baseline`): BASELINE configs[1] -- four-sphere material scene +
+sky box, 1920x1080, 16 launches x num_samples 4 = 64 spp, 10 bounces.  One "step" = one full pass of that workload:
+clear canvas, 16 `render` launches (submitted as one batch, srt_render_batch), one `average`.  At N > 1 (torchrun, one
+rank per GPU) every rank renders its own 16 launches with distinct time seeds (sample sharding, weak scaling), the
+float canvases are reduce-scattered over NCCL, every rank resolves its slice and rank 0 gathers the ARGB8 slices.
 
-Keys printed (one JSON line, rank 0): see the driver contract; plus
-  roofline      bound = fp32 (the path is FP32-pipe bound: SURVEY 8d / BASELINE.md section 2), achieved =
-                counted algorithmic flop per `render` launch / mean launch duration (CUDA events on the
-                launching stream), peak = FMA-chain micro-benchmark measured in this run
-  cpu_baseline  the reference kernel itself (oracle/_ref = render.cl compiled by g++, OpenMP, all host cores) on
-                a bounded sample of the same workload
-  e2e           the same metric through the reference-facing Tracer API with host buffers: per step
-                update_scene (H2D), clear_canvas, 16 x render(ticks, output) each with its ARGB8 read-back
+Beside the headline the same JSON line carries
+  configs       N = 1: the other BASELINE configs (1, 3, 4, 5) at full size, each with its own value, roofline
+                (counted algorithmic flop / launch duration / measured FMA-chain peak) and cpu_baseline (the reference
+                kernel on the host cores; crops for the mesh / 4K configs)
+  strong        N > 1: BASELINE configs[3] (4K, 1024 spp, sample-sharded) and configs[4] (100k-triangle mesh,
+                tile-sharded) at FIXED total work on N GPUs: max-over-ranks wall time including the exchange step
+                (its duration from CUDA events given separately), and the speed-up over the same work on ONE GPU
+                measured in the same run (rank 0 alone)
+  mgpu_parity   N > 1: "ok" iff the tile-sharded image is bit-identical to the 1-GPU image and the sample-sharded
+                canvas is within 1e-5 relative of the 1-GPU canvas, at the full BASELINE sizes; the run FAILS otherwise
+  roofline      bound = fp32 (the path is FP32-pipe bound: SURVEY 8d / BASELINE.md section 2), achieved = counted
+                algorithmic flop per `render` launch / mean launch duration (CUDA events on the launching stream),
+                peak = FMA-chain micro-benchmark measured in this run; fma_pipe = what ncu says the FMA pipe did
+  cpu_baseline  the reference kernel itself (oracle/_ref = render.cl compiled by g++, OpenMP, all host cores) on a
+                bounded sample of the same workload
+  e2e           the same metric through the reference-facing Tracer API with host buffers: per step update_scene
+                (H2D), clear_canvas, 16 x render(ticks, output) each with its ARGB8 read-back
 """
 import argparse
 import json
@@ -38,6 +47,10 @@ from simple_raytracer_b200 import scenes  # noqa: E402
 # nominal algorithmic flop costs, SURVEY.md 8d
 F_SPHERE, F_PLANE, F_MODEL, F_TRI, F_HIT, F_SKY, F_CAM, F_PIX, F_RESOLVE = 19, 14, 24, 46, 147, 75, 47, 6, 20
 METRIC = "Msamples/s (px*spp/s), path-tracing kernel"
+NOMINAL_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
+# CPU-baseline samples of the configs that are too heavy for a full frame on host cores:
+# a centred window of the full-size launch (global pixel ids, seeds and aspect preserved), one launch
+CPU_WINDOWS = {3: (320, 180), 4: (960, 540), 5: (64, 36)}
 
 
 def algorithmic_flops(scene, counters, pixels_launches):
@@ -46,6 +59,26 @@ def algorithmic_flops(scene, counters, pixels_launches):
     per_bounce = F_SPHERE * int((t == 0).sum()) + F_PLANE * int((t == 1).sum()) + F_MODEL * int((t == 2).sum())
     return (counters["samples"] * F_CAM + counters["bounces"] * per_bounce + counters["tri_tests"] * F_TRI +
             counters["hits"] * F_HIT + counters["sky"] * F_SKY + pixels_launches * F_PIX)
+
+
+def host_threads():
+    """Threads for the CPU arm: the cores this process may run on.  Passed explicitly because torchrun exports
+    OMP_NUM_THREADS=1, which would otherwise throttle the reference arm to one core at N > 1."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def kernel_mode(scene):
+    n = scene.shapes["model_num_triangles"][scene.shapes["type"] == 2]
+    return "ANALYTIC" if len(n) == 0 else ("BIG_MODELS" if int(n.max()) > 32 else "SMALL_MODELS")
+
+
+def workload_of(cfg, scene):
+    return {"workload": f"BASELINE config {cfg}: {scene.name}", "resolution": f"{scene.width}x{scene.height}",
+            "spp": scene.spp, "launches": scene.launches, "num_samples": scene.num_samples,
+            "num_bounces": scene.num_bounces, "shapes": int(len(scene.shapes)), "triangles": int(len(scene.triangles))}
 
 
 class ClockSampler:
@@ -84,37 +117,268 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(rows), "reasons": reasons}
 
 
-def cpu_reference_run(scene, sky, steps, warmup, budget_s=4.0):
+# ---------------------------------------------------------------------------------------------- CPU arm
+def cpu_reference_run(scene, sky, steps, warmup, budget_s=4.0, window=None):
     """The reference's CPU path on host cores, all of them.  kind "reference": oracle/_ref, i.e. the
     reference's own src/render.cl compiled by g++ (built in the authoring container, shipped as a .so) with
     the NDRange rows spread over OpenMP threads; kind "port" (only if that library is missing): oracle.c.
-    A step is a bounded sample of the workload: `n` full-frame launches, n chosen so a step takes about
-    budget_s."""
+    A step is a bounded sample of the workload: `n` launches, n chosen so a step takes about budget_s, of the full
+    frame or -- window = (w, h) -- of a centred w x h window of the full-size launch."""
     import oracle
     oracle.build()
-    cores = oracle.max_threads()
+    threads = host_threads()
     impl, kind = ("ref", "reference") if oracle.build_ref() else ("oracle", "port")
+    win = None
+    px = scene.width * scene.height
+    if window:
+        w, h = min(window[0], scene.width), min(window[1], scene.height)
+        x0, y0 = (scene.width - w) // 2, (scene.height - h) // 2
+        win, px = (x0, y0, x0 + w, y0 + h), w * h
+
+    def launch(k, canvas):
+        return oracle.render(scene.render_data(k), scene.scene_data, scene.shapes, scene.triangles, scene.materials,
+                             sky, canvas, window=win, threads=threads, impl=impl)[0]
+
     t0 = time.perf_counter()
-    oracle.render(scene.render_data(0), scene.scene_data, scene.shapes, scene.triangles, scene.materials, sky,
-                  impl=impl)
+    oracle.average(1, launch(0, None), impl=impl)
     t_launch = time.perf_counter() - t0
     n = int(max(1, min(scene.launches, round(budget_s / max(t_launch, 1e-3)))))
-    samples_step = scene.width * scene.height * scene.num_samples * n
+    samples_step = px * scene.num_samples * n
     times = []
+    if n == 1 and warmup == 0 and steps == 1:  # the sizing probe WAS the one step asked for: do not pay for it twice
+        times, steps = [t_launch], 0
     for s in range(warmup + steps):
         canvas = None
         t0 = time.perf_counter()
         for k in range(n):
-            canvas, _ = oracle.render(scene.render_data(k), scene.scene_data, scene.shapes, scene.triangles,
-                                      scene.materials, sky, canvas, impl=impl)
+            canvas = launch(k, canvas)
         oracle.average(n, canvas, impl=impl)
         dt = time.perf_counter() - t0
         if s >= warmup:
             times.append(dt)
     total = sum(times)
     value = samples_step * len(times) / total / 1e6
-    sample = f"{scene.width}x{scene.height} full frame, {n} of {scene.launches} launches x {scene.num_samples} spp per step"
-    return value, total / len(times) * 1e3, cores, sample, kind
+    area = (f"centred {win[2] - win[0]}x{win[3] - win[1]} window of the {scene.width}x{scene.height} launch" if win
+            else f"{scene.width}x{scene.height} full frame")
+    sample = f"{area}, {n} of {scene.launches} launches x {scene.num_samples} spp per step"
+    return value, total / len(times) * 1e3, threads, sample, kind
+
+
+def cpu_baseline_dict(scene, sky, steps=2, warmup=0, budget_s=6.0, window=None):
+    v, _, cores, sample, kind = cpu_reference_run(scene, sky, steps, warmup, budget_s, window)
+    return {"value": v, "unit": "Msamples/s", "cores": cores, "kind": kind, "sample": sample}
+
+
+# ---------------------------------------------------------------------------------------------- CUDA arm
+class Gpu:
+    """Process-wide plumbing of the CUDA arm: torch, the rank layout, barrier."""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py --impl cuda needs a GPU: the product has no CPU path")
+        torch.cuda.set_device(self.local_rank)
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+        self.sky = scenes.procedural_skybox()
+        self.peak_tf = None
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def tracer(self, scene):
+        from simple_raytracer_b200.tracer import Tracer
+        tr = Tracer(scene.width, scene.height, self.sky, device=self.local_rank)
+        tr.scene_data[:] = scene.scene_data
+        tr.update_scene(scene.shapes, scene.triangles, scene.materials)
+        return tr
+
+    def flush_l2(self, stream):
+        with self.torch.cuda.stream(stream):
+            self.flush.zero_()
+
+
+def static_profile(cfg):
+    """Static evidence from the committed ncu capture of this config's render kernel (profiles/roofline_traffic.json):
+    DRAM bytes, warp instructions, FMA-pipe utilisation.  None where no capture is committed."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(f"config{cfg}")
+    except (OSError, ValueError):
+        return None
+
+
+def roofline_of(g, tr, scene, cfg, launch_rds, launch_ms, sm_mhz=None):
+    """Counted algorithmic flop of one launch (untimed instrumented pass, srt_render_counted) / its mean duration."""
+    if g.peak_tf is None:
+        g.peak_tf, g.est_mhz = tr.measure_fp32_peak()
+    cnt = None
+    for rd in launch_rds:
+        cnt = tr.accumulate_counted(rd, cnt)
+    counters = {n: int(cnt[0][n]) for n in cnt.dtype.names}
+    pixels = scene.width * scene.height
+    flops_per_launch = algorithmic_flops(scene, counters, pixels * len(launch_rds)) / len(launch_rds)
+    achieved = flops_per_launch / (launch_ms * 1e-3) / 1e12
+    out = {"bound": "fp32", "kernel": f"srt::render_kernel<COUNT=false, MODE={kernel_mode(scene)}>",
+           "achieved": achieved, "peak": g.peak_tf, "unit": "TFLOP/s", "frac": achieved / g.peak_tf,
+           "peak_source": "FMA-chain micro-benchmark measured in this run (srt_measure_fp32_peak); "
+                          f"nominal 148 SM x 128 x 2 x 1.965 GHz = {NOMINAL_TFLOPS:.1f}",
+           "frac_of_nominal": achieved / NOMINAL_TFLOPS, "flops_per_launch": flops_per_launch, "launch_ms": launch_ms,
+           "counted_launches": len(launch_rds),
+           "Gtests_per_s": counters["tri_tests"] / len(launch_rds) / (launch_ms * 1e-3) / 1e9,
+           "counters": counters, "traffic": None}
+    prof = static_profile(cfg)
+    if prof:
+        # `traffic`: ncu dram__bytes_read + dram__bytes_write of the render kernel + its accumulate epilogue per
+        # reference launch, from the committed capture; `fma_pipe`: what the FMA pipe actually did (the algorithmic
+        # fraction above credits 46 flop per ray-triangle pair the filter decides in ~10 instructions)
+        out["traffic"] = prof.get("dram_bytes_per_launch")
+        out["traffic_source"] = prof.get("capture")
+        for k in ("fma_pipe", "issue_active_pct", "warp_execution_efficiency"):
+            if k in prof:
+                out[k] = prof[k]
+        inst = prof.get("warp_inst_per_launch")
+        if inst:
+            issue_peak = 148 * 4 * (sm_mhz or 1965.0) * 1e6 / 1e9  # G warp-inst/s
+            issue_ach = inst / (launch_ms * 1e-3) / 1e9
+            out["issue"] = {"achieved": issue_ach, "peak": issue_peak, "unit": "G warp-inst/s",
+                            "frac": issue_ach / issue_peak, "warp_inst_per_launch": inst}
+    return out
+
+
+def device_resident(g, tr, scene, rds, steps, warmup, resolve_steps, exchange=None):
+    """`steps` timed passes of clear + one batch of launches + average, inputs resident; CUDA events on the tracer's
+    stream, L2 flushed between passes outside the event pairs.  Returns (ms per step list, kernel ms, launches)."""
+    torch = g.torch
+    stream = torch.cuda.ExternalStream(tr.stream_handle())
+
+    def step():
+        tr.clear_canvas()
+        tr.accumulate_batch(rds)
+        if exchange:
+            exchange()
+        else:
+            tr.resolve_device(resolve_steps)
+
+    for _ in range(warmup):
+        step()
+    g.barrier()
+    tr.render_time_ms()  # drop warm-up launch timings
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    g.barrier()
+    for s in range(steps):
+        g.flush_l2(stream)
+        evs[s][0].record(stream)
+        step()
+        evs[s][1].record(stream)
+    g.barrier()
+    kernel_ms, kernel_launches = tr.render_time_ms()
+    return [a.elapsed_time(b) for a, b in evs], kernel_ms, kernel_launches
+
+
+def config_entry(g, cfg, with_cpu):
+    """One BASELINE config at full size on this GPU: device-resident throughput, roofline, CPU baseline."""
+    scene = scenes.CONFIGS[cfg]()
+    tr = g.tracer(scene)
+    rds = [scene.render_data(k) for k in range(scene.launches)]
+    tr.reserve_batch(rds[0], len(rds))
+    steps, warmup = (20, 3) if cfg == 1 else (1, 1)
+    warm_rds = rds if cfg == 1 else rds[:1]
+    for _ in range(warmup):  # warm-up on one launch for the long configs: the timed pass is seconds long
+        tr.clear_canvas()
+        tr.accumulate_batch(warm_rds)
+    step_ms, kernel_ms, n_launch = device_resident(g, tr, scene, rds, steps, 0, scene.launches)
+    samples = scene.width * scene.height * scene.num_samples * scene.launches
+    total_ms = sum(step_ms)
+    entry = {"config": workload_of(cfg, scene), "value": samples * steps / (total_ms * 1e-3) / 1e6, "unit": "Msamples/s",
+             "ms_per_step": total_ms / steps, "steps": steps, "timing": "CUDA events on the launching stream, device resident",
+             "roofline": roofline_of(g, tr, scene, cfg, rds[:1], kernel_ms / max(n_launch, 1))}
+    if with_cpu:
+        entry["cpu_baseline"] = cpu_baseline_dict(scene, g.sky, steps=1, budget_s=3.0, window=CPU_WINDOWS.get(cfg))
+    tr.close()
+    return entry
+
+
+def strong_entry(g, cfg, mode):
+    """BASELINE configs[3] / configs[4]: FIXED total work on `world` GPUs vs the same work on one GPU (rank 0 alone),
+    both timed in this run as wall clock between barriers (max over ranks), including the exchange step and the
+    read-back of the image into (pinned) host memory.  Also the full-size multi-GPU parity verdict."""
+    from simple_raytracer_b200 import distributed as D
+    torch, world, rank = g.torch, g.world, g.rank
+    scene = scenes.CONFIGS[cfg]()
+    tr = g.tracer(scene)
+    per_rank = -(-scene.launches // world) if mode == "sample" else scene.launches
+    tr.reserve_batch(scene.render_data(0), per_rank)
+    out = np.empty((scene.height, scene.width, 4), np.uint8)
+    tr.pin_output(out)
+
+    def run(rk, wd, launches, timings=None):
+        if mode == "tile":
+            return D.render_tile_sharded(tr, scene, rk, wd, total_launches=launches, output=out, timings=timings)
+        return D.render_sample_sharded(tr, scene, rk, wd, total_launches=launches, output=out, timings=timings)
+
+    run(rank, world, world)  # warm-up: one launch per rank + the exchange step
+    g.barrier()
+    tr.render_time_ms()
+    timings = {}
+    t0 = time.perf_counter()
+    img = run(rank, world, scene.launches, timings)
+    g.barrier()
+    secs_n = g.max_over_ranks(time.perf_counter() - t0)
+    kernel_ms = g.max_over_ranks(tr.render_time_ms()[0])
+    exchange_ms = g.max_over_ranks(timings["exchange_begin"].elapsed_time(timings["exchange_end"]))
+    img_n = img.copy() if rank == 0 else None
+    canvas_n = D.gather_reduced_canvas(tr, rank, world) if mode == "sample" else None
+
+    # the same work on ONE GPU: rank 0 alone, the others wait at the barrier
+    secs_1, parity = None, None
+    if rank == 0:
+        tr.reserve_batch(scene.render_data(0), scene.launches)
+        run(0, 1, 1)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        img_1 = run(0, 1, scene.launches)
+        torch.cuda.synchronize()
+        secs_1 = time.perf_counter() - t0
+        if mode == "tile":
+            parity = {"check": "tile-sharded ARGB8 image bit-identical to the 1-GPU image",
+                      "ok": bool(np.array_equal(img_n, img_1))}
+        else:
+            want = tr.read_canvas()
+            fin = np.isfinite(want) & np.isfinite(canvas_n)
+            rel = float((np.abs(canvas_n - want)[fin] / np.maximum(np.abs(want)[fin], 1e-3)).max())
+            lsb = int(np.abs(img_n.astype(int) - img_1.astype(int)).max())
+            parity = {"check": "sample-sharded canvas within 1e-5 relative of the 1-GPU canvas, image within 1 LSB",
+                      "max_rel": rel, "max_lsb": lsb,
+                      "ok": bool(rel <= 1e-5 and lsb <= 1 and np.array_equal(np.isfinite(want), np.isfinite(canvas_n)))}
+    g.barrier()
+    tr.close()
+    samples = scene.width * scene.height * scene.num_samples * scene.launches
+    if rank != 0:
+        return None
+    return {"config": workload_of(cfg, scene), "sharding": mode, "n_gpus": world, "scaling": "strong",
+            "seconds": secs_n, "value": samples / secs_n / 1e6, "unit": "Msamples/s",
+            "max_rank_kernel_ms": kernel_ms, "exchange_ms": exchange_ms,
+            "exchange": ("reduce-scatter of float canvases + per-rank average + gather of ARGB8 slices" if mode == "sample"
+                         else "MAX-reduce of per-rank ARGB8 band images"),
+            "seconds_n1": secs_1, "value_n1": samples / secs_1 / 1e6, "speedup_vs_n1": secs_1 / secs_n,
+            "timing": "wall clock between barriers, max over ranks; includes the exchange step and the image read-back",
+            "parity": parity}
 
 
 def main():
@@ -125,20 +389,15 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--config", type=int, default=2, help="BASELINE config index 1..5 (default 2 = configs[1])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="headline only: skip `configs` (N = 1) / `strong` (N > 1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cuda" else args.warmup
 
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-
     scene = scenes.CONFIGS[args.config]()
-    workload = {"workload": f"BASELINE config {args.config}: {scene.name}", "resolution": f"{scene.width}x{scene.height}",
-                "spp": scene.spp, "launches": scene.launches, "num_samples": scene.num_samples,
-                "num_bounces": scene.num_bounces, "shapes": int(len(scene.shapes)), "triangles": int(len(scene.triangles))}
+    workload = workload_of(args.config, scene)
 
     if args.impl == "reference":
-        if rank != 0:
+        if int(os.environ.get("RANK", "0")) != 0:
             return 0
         sky = scenes.procedural_skybox()
         value, ms, cores, sample, kind = cpu_reference_run(scene, sky, args.steps, args.warmup)
@@ -154,72 +413,30 @@ def main():
                      "oracle/_ref is missing: oracle/oracle.c, the scalar C restatement of render.cl, OpenMP over rows")}))
         return 0
 
-    import torch
-    import torch.distributed as dist
-    from simple_raytracer_b200 import distributed as srt_dist
-    from simple_raytracer_b200.tracer import Tracer
-
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py --impl cuda needs a GPU: the product has no CPU path")
-    torch.cuda.set_device(local_rank)
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    sky = scenes.procedural_skybox()
-    tr = Tracer(scene.width, scene.height, sky, device=local_rank)
-    tr.scene_data[:] = scene.scene_data
-    tr.update_scene(scene.shapes, scene.triangles, scene.materials)
-    stream = torch.cuda.ExternalStream(tr.stream_handle())
+    from simple_raytracer_b200 import distributed as D
+    g = Gpu()
+    torch, dist, rank, world = g.torch, g.dist, g.rank, g.world
+    tr = g.tracer(scene)
     L = scene.launches
     my_rds = [scene.render_data(k * world + rank) for k in range(L)]  # distinct time seeds per rank
     pixels = scene.width * scene.height
     samples_per_rank_step = pixels * scene.num_samples * L
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
-
-    def device_step():
-        tr.clear_canvas()
-        tr.accumulate_batch(my_rds)  # the step's 16 launches, one persistent kernel (srt_render_batch)
-        if world > 1:
-            srt_dist.reduce_canvas(tr, dst=0)
-        if rank == 0:
-            tr.resolve_device(L * world)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    tr.reserve_batch(my_rds[0], L)
 
     # ---- device-resident arm -----------------------------------------------------------------
-    for _ in range(args.warmup):
-        device_step()
-    barrier()
-    tr.render_time_ms()  # drop warm-up launch timings
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    exchange = (lambda: D.reduce_scatter_resolve(tr, L * world, rank, world, read_back=False)) if world > 1 else None
+    sampler = ClockSampler(g.local_rank) if rank == 0 else None
     time.sleep(0.25)
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
     t_region0 = time.perf_counter()
-    for s in range(args.steps):
-        with torch.cuda.stream(stream):
-            flush.zero_()  # L2 flush between timed iterations, outside the event pair
-        evs[s][0].record(stream)
-        device_step()
-        evs[s][1].record(stream)
-    barrier()
+    step_ms, kernel_ms, kernel_launches = device_resident(g, tr, scene, my_rds, args.steps, args.warmup, L, exchange)
     t_region1 = time.perf_counter()
-    step_ms = [a.elapsed_time(b) for a, b in evs]
-    my_ms = sum(step_ms)
-    kernel_ms, kernel_launches = tr.render_time_ms()
     clocks = sampler.stop(t_region0, t_region1) if sampler else None
-    tmax = torch.tensor([my_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    total_ms = float(tmax.item())
+    total_ms = g.max_over_ranks(sum(step_ms))
     value = samples_per_rank_step * world * args.steps / (total_ms * 1e-3) / 1e6
 
     # ---- end-to-end arm: the reference-facing Tracer protocol with host buffers -----------------
     output = np.empty(pixels * 4, np.uint8)
+    tr.pin_output(output)  # the caller's one `pixels` vector (src/main.cpp:128), page-locked once at start-up
     h2d = scene.shapes.nbytes + scene.triangles.nbytes + scene.materials.nbytes + 96 + L * 112
     d2h = L * pixels * 4
 
@@ -231,87 +448,68 @@ def main():
             tr.render(i + 1, output)                                      # src/main.cpp:290
 
     e2e_step()
-    barrier()
+    g.barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         e2e_step()
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = samples_per_rank_step * world * args.steps / float(te.item()) / 1e6
+    g.barrier()
+    e2e_value = samples_per_rank_step * world * args.steps / g.max_over_ranks(time.perf_counter() - t0) / 1e6
+    tr.unpin_output()
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return 0
-
-    # ---- roofline of the dominant kernel (untimed instrumented pass) ------------------------------
-    peak_tf, est_mhz = tr.measure_fp32_peak()
-    cnt = None
-    for rd in my_rds:
-        cnt = tr.accumulate_counted(rd, cnt)
-    counters = {n: int(cnt[0][n]) for n in cnt.dtype.names}
-    flops_per_launch = algorithmic_flops(scene, counters, pixels * L) / L
-    launch_ms = kernel_ms / max(kernel_launches, 1)
-    achieved = flops_per_launch / (launch_ms * 1e-3) / 1e12
-    nominal = 148 * 128 * 2 * 1.965e9 / 1e12
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except OSError:
-        pass
-    canvas_bytes = pixels * 32  # canvas RMW per launch: the only HBM-resident traffic of the kernel
-    roofline = {"bound": "fp32", "kernel": "srt::render_kernel<COUNT=false, MODE=%s>" % ("BIG_MODELS" if len(scene.triangles) > 32 else ("SMALL_MODELS" if len(scene.triangles) else "ANALYTIC")), "achieved": achieved, "peak": peak_tf,
-                "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,
-                "peak_source": "FMA-chain micro-benchmark measured in this run (srt_measure_fp32_peak); "
-                               f"nominal 148 SM x 128 x 2 x 1.965 GHz = {nominal:.1f}",
-                "frac_of_nominal": achieved / nominal, "flops_per_launch": flops_per_launch,
-                "launch_ms": launch_ms, "launches_timed": int(kernel_launches),
-                "kernel_share_of_step": kernel_ms / total_ms if total_ms else None,
-                "hbm": {"algorithmic_bytes_per_launch": canvas_bytes,
-                        "achieved_gbs": canvas_bytes / (launch_ms * 1e-3) / 1e9,
-                        "peak_gbs": peaks.get("hbm_gbs", 6650.0),
-                        "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback B200_PROFILING.md"},
-                "traffic": None, "counters": counters}
-    # static evidence from the committed ncu capture of the same launch (profiles/): DRAM traffic, and the view that
-    # actually bounds these kernels -- warp-instruction issue (4 schedulers x 1 inst/clk per SM)
-    prof = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-    if os.path.exists(prof):
+    # ---- roofline of the dominant kernel (untimed instrumented pass), CPU baseline ---------------
+    roofline = cpu_baseline = None
+    if rank == 0:
+        roofline = roofline_of(g, tr, scene, args.config, my_rds, kernel_ms / max(kernel_launches, 1),
+                               clocks["sm_mhz"] if clocks else None)
+        roofline["launches_timed"] = int(kernel_launches)
+        roofline["kernel_share_of_step"] = kernel_ms / sum(step_ms)
+        peaks = {}
         try:
-            pj = json.load(open(prof))
-            roofline["traffic"] = pj.get(f"config{args.config}")
-            inst = pj.get(f"config{args.config}_inst_executed")
-            if inst:
-                issue_peak = 148 * 4 * (clocks["sm_mhz"] or 1965.0) * 1e6 / 1e9  # G warp-inst/s
-                issue_ach = inst / (launch_ms * 1e-3) / 1e9
-                roofline["issue"] = {"achieved": issue_ach, "peak": issue_peak, "unit": "G warp-inst/s",
-                                     "frac": issue_ach / issue_peak, "warp_inst_per_launch": inst,
-                                     "source": pj.get(f"config{args.config}_capture")}
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except (OSError, ValueError):
             pass
+        canvas_bytes = pixels * 32  # canvas RMW per launch: the only HBM-resident traffic the algorithm needs
+        roofline["hbm"] = {"algorithmic_bytes_per_launch": canvas_bytes,
+                           "achieved_gbs": canvas_bytes / (roofline["launch_ms"] * 1e-3) / 1e9,
+                           "peak_gbs": peaks.get("hbm_gbs", 6650.0),
+                           "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback B200_PROFILING.md"}
+        if not args.no_cpu_baseline:
+            cpu_baseline = cpu_baseline_dict(scene, g.sky)
+    tr.close()
 
-    cpu_baseline = None
-    if not args.no_cpu_baseline:
-        v, ms, cores, sample, kind = cpu_reference_run(scene, sky, steps=2, warmup=0, budget_s=6.0)
-        cpu_baseline = {"value": v, "unit": "Msamples/s", "cores": cores, "kind": kind, "sample": sample}
+    # ---- the other BASELINE configs (N = 1) / strong scaling + parity of configs[3], [4] (N > 1) --
+    configs, strong, mgpu_parity = None, None, None
+    if not args.no_extras:
+        if world == 1:
+            configs = [config_entry(g, c, not args.no_cpu_baseline) for c in (1, 3, 4, 5) if c != args.config]
+        else:
+            strong = [strong_entry(g, 4, "sample"), strong_entry(g, 5, "tile")]
+            if rank == 0:
+                mgpu_parity = "ok" if all(s["parity"]["ok"] for s in strong) else "FAILED"
 
-    print(json.dumps({
-        "metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": dict(workload, parallelism=f"sample-sharded x{world}" if world > 1 else "single GPU",
-                       l2="flushed between timed steps (256 MiB memset, outside the event pairs)",
-                       timing="CUDA events per step on the launching stream, summed; max over ranks"),
-        "clocks": clocks, "gpu_launches": args.steps * 3,  # per step: render (16 launches batched) + accumulate + average
-        "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "api": "Tracer.update_scene + clear_canvas + 16 x Tracer.render(ticks, host_output) per step, wall clock"},
-        "roofline": roofline, "cpu_baseline": cpu_baseline,
-        "fp32_peak_measured_tflops": peak_tf, "sm_clock_est_mhz": est_mhz}))
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload,
+            "run": {"parallelism": f"sample-sharded x{world}: every rank renders its own {L} launches" if world > 1 else "single GPU",
+                    "l2": "flushed between timed steps (256 MiB memset, outside the event pairs)",
+                    "timing": "CUDA events per step on the launching stream, summed; max over ranks"},
+            "clocks": clocks,
+            "gpu_launches": args.steps * 3,  # per step: render (16 launches batched) + accumulate + average
+            "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "api": "Tracer.update_scene + clear_canvas + 16 x Tracer.render(ticks, host_output) per step, wall clock; "
+                           "the output vector is page-locked once with Tracer.pin_output"},
+            "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "fp32_peak_measured_tflops": g.peak_tf, "sm_clock_est_mhz": getattr(g, "est_mhz", None),
+            "configs": configs, "strong": strong, "mgpu_parity": mgpu_parity}))
+    failed = world > 1 and not args.no_extras and rank == 0 and mgpu_parity != "ok"
     if world > 1:
+        flag = torch.tensor([1 if failed else 0], device="cuda")
+        dist.broadcast(flag, 0)
+        failed = bool(int(flag.item()))
         dist.destroy_process_group()
-    return 0
+    return 1 if failed else 0
 
 
 if __name__ == "__main__":

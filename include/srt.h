@@ -132,6 +132,16 @@ int srt_reserve_batch(srt_tracer *t, const srt_render_data *rd, size_t n);
  * argb_out receives width*height*4 bytes in A,R,G,B order (render.cl:525-535).  Synchronises. */
 int srt_resolve(srt_tracer *t, uint32_t num_steps, uint8_t *argb_out);
 
+/* Optional: page-lock ONE caller-owned output buffer so that srt_resolve / srt_render_frame / srt_read_output copy
+ * straight into it instead of through the handle's pinned staging buffer (saves a host memcpy of width*height*4
+ * bytes per frame).  The reference's caller allocates its `pixels` vector once and hands it in every frame
+ * (src/main.cpp:128,290), which is the case this is for.  The library never pins memory on its own: the CALLER
+ * guarantees that [buffer, buffer+bytes) stays allocated until srt_unpin_output, a second srt_pin_output, or
+ * srt_destroy -- freeing it while pinned is undefined behaviour (CUDA's rule for cudaHostRegister).  Reads into
+ * any other address keep using the staging path. */
+int srt_pin_output(srt_tracer *t, void *buffer, size_t bytes);
+int srt_unpin_output(srt_tracer *t);
+
 /* Tracer::render(ticks_stopped, output) in one call: srt_render + srt_resolve. */
 int srt_render_frame(srt_tracer *t, const srt_render_data *rd, uint32_t ticks_stopped, uint8_t *argb_out);
 
@@ -146,6 +156,9 @@ int srt_write_canvas(srt_tracer *t, const float *rgba_in);         /* restore an
 int srt_canvas_device_ptr(srt_tracer *t, void **ptr, size_t *bytes); /* for NCCL reduce of per-GPU canvases */
 int srt_output_device_ptr(srt_tracer *t, void **ptr, size_t *bytes); /* ARGB8 buffer, for gathers */
 int srt_resolve_device(srt_tracer *t, uint32_t num_steps);         /* `average` without the read-back */
+/* `average` over pixels [first_pixel, first_pixel + count) only: after a reduce-scatter of per-GPU canvases every
+ * GPU resolves the slice it owns (sample sharding). */
+int srt_resolve_device_range(srt_tracer *t, uint32_t num_steps, size_t first_pixel, size_t count);
 int srt_read_output(srt_tracer *t, uint8_t *argb_out);             /* read-back of the ARGB8 buffer alone; synchronises */
 int srt_stream(srt_tracer *t, void **cuda_stream);
 int srt_synchronize(srt_tracer *t);

@@ -66,6 +66,12 @@ class Tracer {
 		check(srt_render_frame(handle_, &options, ticks_stopped, output.data()));
 	}
 
+	// Optional (srt_pin_output): page-lock the `pixels` vector that is handed to render() every frame
+	// (src/main.cpp:128,290) so the read-back lands in it directly.  The vector must not be resized or destroyed
+	// before unpin_output() or this Tracer's destructor.
+	void pin_output(std::vector<uint8_t> &output) { check(srt_pin_output(handle_, output.data(), output.size())); }
+	void unpin_output() { check(srt_unpin_output(handle_)); }
+
 	srt_tracer *handle() { return handle_; }
 
   private:

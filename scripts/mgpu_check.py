@@ -1,5 +1,6 @@
 """Multi-GPU check, run under torchrun (one rank per GPU):
-  * sample sharding (config-4 style): canvas vs the 1-GPU canvas within 1e-5 relative, image within 1 LSB;
+  * sample sharding (config-4 style), both exchange steps (reduce-scatter + per-rank resolve + gather; reduce to
+    root): canvas vs the 1-GPU canvas within 1e-5 relative, image within 1 LSB;
   * tile sharding (config-5 style): ARGB8 image bit-identical to the 1-GPU image.
 Prints one JSON line on rank 0; exits non-zero on mismatch."""
 import json
@@ -34,9 +35,12 @@ def main():
     # -- sample sharding
     sc = scenes.config2(640, 360, num_samples=4, launches=8)
     tr = tracer_for(sc)
-    img = D.render_sample_sharded(tr, sc, rank, world)
+    img = D.render_sample_sharded(tr, sc, rank, world)  # reduce-scatter tail: every rank owns a reduced slice
+    canvas = D.gather_reduced_canvas(tr, rank, world)
+    img_root = D.render_sample_sharded(tr, sc, rank, world, tail="reduce")  # reduce-to-root tail
     if rank == 0:
-        canvas = tr.read_canvas()
+        report["tails_agree_lsb"] = int(np.abs(img.astype(int) - img_root.astype(int)).max())
+        ok &= report["tails_agree_lsb"] <= 1
         one = tracer_for(sc)
         want_img = D.render_sample_sharded(one, sc, 0, 1)
         want = one.read_canvas()

@@ -4,7 +4,8 @@
 // (:55-135), save_ppm (:4-15) -- and Model::compute_bounding_box (src/shape.cpp:45-58), producing the
 // same 96-byte Triangle records (include/srt.h) that srt_upload_scene turns into device SoA buffers.
 // Differences from the reference, all on inputs the reference mishandles:
-//   * files are validated (short reads, index ranges) and errors are returned instead of crashing;
+//   * files are validated (short reads, a triangle count the file is too short for, index ranges) and errors are
+//     returned instead of crashing; no C++ exception leaves an extern "C" function;
 //   * OBJ negative indices count back from the end of the list (the reference computes len-idx+1);
 //   * OBJ faces without normals get the flat geometric normal (the reference reads an
 //     uninitialised index); faces with more than 3 corners are fan-triangulated (the reference
@@ -14,6 +15,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <string>
 #include <vector>
 
@@ -87,10 +89,7 @@ extern "C" {
 
 void srt_free(void *p) { free(p); }
 
-int srt_load_stl(const char *path, srt_triangle **triangles, size_t *count) {
-	if (!path || !triangles || !count) return SRT_ERR_INVALID;
-	*triangles = nullptr;
-	*count = 0;
+static int load_stl(const char *path, srt_triangle **triangles, size_t *count) {
 	FILE *f = fopen(path, "rb");
 	if (!f) return SRT_ERR_INVALID;  // reference returns nullopt, parser.cpp:20-22
 	uint8_t header[84];
@@ -100,6 +99,13 @@ int srt_load_stl(const char *path, srt_triangle **triangles, size_t *count) {
 	}
 	uint32_t n;
 	memcpy(&n, header + 80, 4);
+	// the count comes from the file: it must fit the bytes that are actually there before anything is reserved
+	long size = -1;
+	if (fseek(f, 0, SEEK_END) == 0) size = ftell(f);
+	if (size < 84 || (uint64_t)n > (uint64_t)(size - 84) / 50 || fseek(f, 84, SEEK_SET) != 0) {
+		fclose(f);
+		return SRT_ERR_INVALID;
+	}
 	std::vector<srt_triangle> tris;
 	tris.reserve(n);
 	for (uint32_t i = 0; i < n; ++i) {
@@ -119,10 +125,18 @@ int srt_load_stl(const char *path, srt_triangle **triangles, size_t *count) {
 	return hand_over(tris, triangles, count);
 }
 
-int srt_load_obj(const char *path, srt_triangle **triangles, size_t *count) {
+int srt_load_stl(const char *path, srt_triangle **triangles, size_t *count) {
 	if (!path || !triangles || !count) return SRT_ERR_INVALID;
 	*triangles = nullptr;
 	*count = 0;
+	try {
+		return load_stl(path, triangles, count);
+	} catch (const std::exception &) {  // bad_alloc and friends must not cross the C boundary
+		return SRT_ERR_INVALID;
+	}
+}
+
+static int load_obj(const char *path, srt_triangle **triangles, size_t *count) {
 	FILE *f = fopen(path, "r");
 	if (!f) return SRT_ERR_INVALID;
 	std::vector<V3> verts, normals;
@@ -205,8 +219,18 @@ int srt_load_obj(const char *path, srt_triangle **triangles, size_t *count) {
 	return hand_over(tris, triangles, count);
 }
 
-int srt_save_ppm(const char *path, const uint8_t *argb, int width, int height) {
-	if (!path || !argb || width <= 0 || height <= 0) return SRT_ERR_INVALID;
+int srt_load_obj(const char *path, srt_triangle **triangles, size_t *count) {
+	if (!path || !triangles || !count) return SRT_ERR_INVALID;
+	*triangles = nullptr;
+	*count = 0;
+	try {
+		return load_obj(path, triangles, count);
+	} catch (const std::exception &) {
+		return SRT_ERR_INVALID;
+	}
+}
+
+static int save_ppm(const char *path, const uint8_t *argb, int width, int height) {
 	FILE *f = fopen(path, "wb");
 	if (!f) return SRT_ERR_INVALID;
 	fprintf(f, "P6 %d %d 255\n", width, height);  // parser.cpp:7-8
@@ -227,6 +251,15 @@ int srt_save_ppm(const char *path, const uint8_t *argb, int width, int height) {
 	return SRT_OK;
 }
 
+int srt_save_ppm(const char *path, const uint8_t *argb, int width, int height) {
+	if (!path || !argb || width <= 0 || height <= 0) return SRT_ERR_INVALID;
+	try {
+		return save_ppm(path, argb, width, height);
+	} catch (const std::exception &) {
+		return SRT_ERR_INVALID;
+	}
+}
+
 int srt_model_bounds(const srt_triangle *triangles, size_t n_triangles, srt_model *model) {
 	if (!model || (!triangles && n_triangles)) return SRT_ERR_INVALID;
 	if ((size_t)model->triangle_index + model->num_triangles > n_triangles) return SRT_ERR_INVALID;
@@ -236,10 +269,12 @@ int srt_model_bounds(const srt_triangle *triangles, size_t n_triangles, srt_mode
 		const srt_triangle &t = triangles[model->triangle_index + i];
 		for (int j = 0; j < 3; ++j) {
 			const srt_float3 &p = t.vertices[j].pos;
-			// same operation order as the device pre-transform (render.cl:114-120 with w = 1)
-			float w[3] = {std::fmaf(m[3].x, 1.0f, std::fmaf(m[2].x, p.z, std::fmaf(m[1].x, p.y, m[0].x * p.x))),
-			              std::fmaf(m[3].y, 1.0f, std::fmaf(m[2].y, p.z, std::fmaf(m[1].y, p.y, m[0].y * p.x))),
-			              std::fmaf(m[3].z, 1.0f, std::fmaf(m[2].z, p.z, std::fmaf(m[1].z, p.y, m[0].z * p.x)))};
+			// the operations of the device pre-transform (prepare_triangles_kernel; render.cl:114-120 with w = 1):
+			// every product and sum rounded on its own (this file is built with -ffp-contract=off), so the box
+			// encloses exactly the world-space vertices the kernel intersects
+			float w[3] = {m[0].x * p.x + m[1].x * p.y + m[2].x * p.z + m[3].x * 1.0f,
+			              m[0].y * p.x + m[1].y * p.y + m[2].y * p.z + m[3].y * 1.0f,
+			              m[0].z * p.x + m[1].z * p.y + m[2].z * p.z + m[3].z * 1.0f};
 			for (int c = 0; c < 3; ++c) {
 				mn[c] = w[c] < mn[c] ? w[c] : mn[c];
 				mx[c] = w[c] > mx[c] ? w[c] : mx[c];

@@ -64,6 +64,9 @@ struct DevScene {
 // the fresh rays of the next instead of idling lanes (a 1080p x 4-sample launch is 4.5 % slower per sample than a
 // 64-sample one; an eighth of it, one GPU's share under tile sharding, 25 %).
 constexpr int MAX_BATCH = 16;
+// Work items (launch, pixel, sample) of one kernel.  Item indices are 32 bits; the global cursor they are dealt from
+// is 64 bits, so overshooting it is harmless, and base + lane (base < MAX_ITEMS, lane < 32) cannot wrap either.
+constexpr unsigned long long MAX_ITEMS = 0xffffff00ull;
 struct RenderParams {
 	int width, height, num_samples, num_bounces;
 	float aspect_ratio, fov_scale;
@@ -409,20 +412,23 @@ __device__ __forceinline__ void scatter(const DevScene &sc, int material, vec3 p
 #endif
 constexpr int RENDER_THREADS = SRT_RENDER_THREADS;
 
-// Dense triangle phase: a register-tiled outer product of (parked rays) x (one model's triangles).
+// Dense triangle phase: a register-tiled outer product of (parked rays) x (one model's triangles), in two stages --
+// a cheap conservative FILTER over all pairs, then the reference's exact Moller-Trumbore on the few it lets through.
 //
-//   * the model's hot stream (48 B per triangle: v0, e1, e2) arrives in a per-warp ring of
-//     shared-memory tiles filled by 1-D bulk async copies (cp.async.bulk -> SASS UBLKCP) completing on
-//     an mbarrier, TILE_STAGES tiles ahead of the consumer: no lane issues a global load;
-//   * every lane lifts TRIS_PER_LANE triangles of the current tile into REGISTERS (conflict-free
-//     LDS.128), so all 32 lanes are busy however few rays are parked;
-//   * the parked rays (origin, direction: 2 x float4 published once per phase) are broadcast one
-//     after the other; for each ray every lane runs the division-free filter on its own triangles
-//     and one VOTE per triangle slot hands the survivor mask of 32 triangles to the ray's owner lane;
-//   * after the sweep of a tile each owner runs the exact Moller-Trumbore on its few survivors, in
-//     triangle order, so ties resolve exactly as in the reference loop (render.cl:324-350).
-// Shared-memory traffic is 32 B per ray per tile instead of 48 B per ray per triangle, which is what
-// moves the loop from the shared-memory crossbar limit to the issue limit.
+//   * the model's 40-byte filter records (TriFlt: n' = e2 x e1, m = e2 x v0, e2, margin scale g) arrive in a per-warp
+//     ring of shared-memory tiles filled by 1-D bulk async copies (cp.async.bulk -> SASS UBLKCP) completing on an
+//     mbarrier, TILE_STAGES tiles ahead of the consumer: no lane issues a global load for the sweep;
+//   * every lane lifts TRIS_PER_LANE triangles of the current tile into REGISTERS (40 B stride: conflict-free
+//     LDS.64), so all 32 lanes are busy however few rays are parked;
+//   * the parked rays (3 x float4 each: d duplicated for the packed FP32x2 chain, c = o x d, o; published once per
+//     phase) are broadcast two per trip; every lane runs tri_filter_sweep on its own triangles and one VOTE per
+//     triangle slot hands the 32-bit survivor mask to the ray's owner lane;
+//   * after a tile the owners expand their masks into a per-warp ring of (ray << 27 | triangle) PAIRS, and the ring
+//     is drained 32 pairs at a time by ALL lanes: tri_exact on the reference operands (tri_hot, LDG.128 x 3 through
+//     L1/L2), folded into best[ray] by a shared-memory atomicMin on (t bits << 32 | triangle + 1), which keeps the
+//     closest hit and, on equal t, the lowest triangle index -- the order of the sequential loop, render.cl:324-350.
+// Shared-memory traffic is 48 B per ray per tile instead of 40 B per ray per triangle, which is what moves the loop
+// from the shared-memory crossbar limit to the issue limit.
 #ifndef SRT_TRIS_PER_LANE
 #define SRT_TRIS_PER_LANE 4
 #endif
@@ -690,7 +696,7 @@ enum { MODE_ANALYTIC = 0, MODE_SMALL_MODELS = 1, MODE_BIG_MODELS = 2 };
 template <bool COUNT, int MODE>
 __global__ void __launch_bounds__(RENDER_THREADS, MODE == MODE_BIG_MODELS ? SRT_MIN_BLOCKS : SRT_MIN_BLOCKS_ANALYTIC)
 render_kernel(const __grid_constant__ RenderParams p, const __grid_constant__ DevScene sc,
-              float4 *__restrict__ scratch, unsigned int *__restrict__ cursor, Counters *__restrict__ counters) {
+              float4 *__restrict__ scratch, unsigned long long *__restrict__ cursor, Counters *__restrict__ counters) {
 	const unsigned FULL = 0xffffffffu;
 	const int lane = threadIdx.x & 31;
 	Counters cnt = {0, 0, 0, 0, 0, 0};
@@ -759,11 +765,16 @@ render_kernel(const __grid_constant__ RenderParams p, const __grid_constant__ De
 		if (QUEUES && need) {
 			const int want = __popc(need);
 			if (ray_count < want && !exhausted) {  // generate 32 camera paths with every lane active
+				// the cursor is 64 bits wide, so the one step every warp takes past the end can never wrap it back
+				// into the item range; past the end the base collapses to a sentinel (total_items <= MAX_ITEMS)
 				unsigned int base = 0;
-				if (lane == 0) base = atomicAdd(cursor, 32u);
+				if (lane == 0) {
+					const unsigned long long b = atomicAdd(cursor, 32ull);
+					base = b < (unsigned long long)p.total_items ? (unsigned int)b : 0xffffffffu;
+				}
 				base = __shfl_sync(FULL, base, 0);
 				const unsigned int it = base + lane;
-				const bool valid = it < p.total_items;
+				const bool valid = base != 0xffffffffu && it < p.total_items;
 				const unsigned vm = __ballot_sync(FULL, valid);
 				if (valid) {
 					uint32_t sd;
@@ -806,11 +817,14 @@ render_kernel(const __grid_constant__ RenderParams p, const __grid_constant__ De
 		}
 		if (!QUEUES && need) {
 			unsigned int base = 0;
-			if (lane == 0) base = atomicAdd(cursor, (unsigned int)__popc(need));
+			if (lane == 0) {  // 64-bit cursor, see above
+				const unsigned long long b = atomicAdd(cursor, (unsigned long long)__popc(need));
+				base = b < (unsigned long long)p.total_items ? (unsigned int)b : 0xffffffffu;
+			}
 			base = __shfl_sync(FULL, base, 0);
 			if (need_item) {
 				item = base + __popc(need & ((1u << lane) - 1u));
-				if (item < p.total_items) {  // start path `sample` of pixel `pix`, :496-516
+				if (base != 0xffffffffu && item < p.total_items) {  // start path `sample` of pixel `pix`, :496-516
 					start_path(p, item, seed, o, d);
 					mask = mk(1, 1, 1);
 					color = mk(0, 0, 0);

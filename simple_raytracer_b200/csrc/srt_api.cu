@@ -65,12 +65,13 @@ struct srt_tracer {
 
 	float4 *canvas = nullptr;  // float3 with 16-byte stride (tracer.cpp:39)
 	uchar4 *output = nullptr;  // ARGB8 (tracer.cpp:40)
-	uint8_t *pinned_out = nullptr;
-	void *registered_out = nullptr;  // caller's output vector, page-locked once it is seen twice in a row
-	void *last_out = nullptr;
+	uint8_t *pinned_out = nullptr;   // staging buffer of every read-back into memory the library does not own
+	void *registered_out = nullptr;  // srt_pin_output: a caller buffer page-locked at the CALLER's request
+	size_t registered_bytes = 0;
+	cudaEvent_t chunk_ev[4] = {nullptr, nullptr, nullptr, nullptr};  // read-back pipeline (read_back)
 	float4 *sky = nullptr;
 	int sky_w = 0, sky_h = 0;
-	unsigned int *cursor = nullptr;
+	unsigned long long *cursor = nullptr;  // 64 bits: lanes may step past the last item without ever wrapping
 	srt::Counters *counters = nullptr;
 
 	DevBuf<int4> shape_hdr;
@@ -173,8 +174,8 @@ int make_params(srt_tracer *t, const srt_render_data *rd, srt::RenderParams &p) 
 	}
 	p.my_rows = rows;
 	p.total_pixels = (unsigned int)rows * (unsigned int)rd->width;
-	if ((unsigned long long)p.total_pixels * (unsigned long long)rd->num_samples > 0xfffffff0ull)
-		return fail(t, SRT_ERR_INVALID, "width*height*num_samples exceeds 2^32 work items per launch");
+	if ((unsigned long long)p.total_pixels * (unsigned long long)rd->num_samples > srt::MAX_ITEMS)
+		return fail(t, SRT_ERR_INVALID, "width*height*num_samples exceeds %llu work items per launch", srt::MAX_ITEMS);
 	p.items_per_launch = p.total_pixels * (unsigned int)rd->num_samples;
 	p.total_items = p.items_per_launch;
 	return SRT_OK;
@@ -191,7 +192,8 @@ int launch_render_impl(srt_tracer *t, const srt::RenderParams &p) {
 		SRT_CUDA(t, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, srt::RENDER_THREADS, smem));
 		grid = std::max(per_sm, 1) * t->sm_count;  // persistent: one full wave, work pulled from the cursor
 	}
-	SRT_CUDA(t, cudaMemsetAsync(t->cursor, 0, sizeof(unsigned int), t->stream));
+	SRT_CUDA(t, t->scratch.reserve(p.total_items));
+	SRT_CUDA(t, cudaMemsetAsync(t->cursor, 0, sizeof(unsigned long long), t->stream));
 	std::pair<cudaEvent_t, cudaEvent_t> ev;
 	if (!t->event_pool.empty()) {
 		ev = t->event_pool.back();
@@ -201,12 +203,15 @@ int launch_render_impl(srt_tracer *t, const srt::RenderParams &p) {
 		SRT_CUDA(t, cudaEventCreate(&ev.second));
 	}
 	const srt::DevScene sc = dev_scene(t);
-	SRT_CUDA(t, t->scratch.reserve(p.total_items));
-	SRT_CUDA(t, cudaEventRecord(ev.first, t->stream));
+	cudaError_t le = cudaEventRecord(ev.first, t->stream);
 	kernel<<<grid, srt::RENDER_THREADS, smem, t->stream>>>(p, sc, t->scratch.ptr, t->cursor, t->counters);
 	srt::accumulate_kernel<<<(p.total_pixels + 255) / 256, 256, 0, t->stream>>>(p, t->scratch.ptr, t->canvas);
-	SRT_CUDA(t, cudaEventRecord(ev.second, t->stream));
-	SRT_CUDA(t, cudaGetLastError());
+	if (le == cudaSuccess) le = cudaEventRecord(ev.second, t->stream);
+	if (le == cudaSuccess) le = cudaGetLastError();
+	if (le != cudaSuccess) {
+		t->event_pool.push_back(ev);  // the pair goes back to the pool on every path
+		return fail(t, SRT_ERR_CUDA, "render launch failed: %s", cudaGetErrorString(le));
+	}
 	if (t->timing.size() >= 4096) {  // nobody is reading the timings: recycle
 		for (auto &e : t->timing) t->event_pool.push_back(e);
 		t->timing.clear();
@@ -287,7 +292,8 @@ int srt_create(int width, int height, const float *skybox_rgba, int sky_w, int s
 	CREATE_CUDA(cudaMalloc(&t->canvas, n * sizeof(float4)));
 	CREATE_CUDA(cudaMalloc(&t->output, n * sizeof(uchar4)));
 	CREATE_CUDA(cudaMallocHost(&t->pinned_out, n * 4));
-	CREATE_CUDA(cudaMalloc(&t->cursor, sizeof(unsigned int)));
+	CREATE_CUDA(cudaMalloc(&t->cursor, sizeof(unsigned long long)));
+	for (auto &e : t->chunk_ev) CREATE_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 	CREATE_CUDA(cudaMalloc(&t->counters, sizeof(srt::Counters)));
 	CREATE_CUDA(cudaMalloc(&t->sky, (size_t)sky_w * sky_h * sizeof(float4)));
 	CREATE_CUDA(cudaMemcpyAsync(t->sky, skybox_rgba, (size_t)sky_w * sky_h * sizeof(float4), cudaMemcpyHostToDevice, t->stream));
@@ -309,6 +315,8 @@ int srt_destroy(srt_tracer *t) {
 		cudaEventDestroy(e.second);
 	}
 	if (t->registered_out) cudaHostUnregister(t->registered_out);
+	for (auto &e : t->chunk_ev)
+		if (e) cudaEventDestroy(e);
 	cudaGetLastError();
 	cudaFree(t->canvas);
 	cudaFree(t->output);
@@ -369,6 +377,10 @@ int srt_upload_scene(srt_tracer *t, const srt_shape *shapes, size_t n_shapes, co
 		}
 	}
 
+	// From here on the device buffers are being replaced: until the last copy has landed the handle has NO scene, so
+	// a failure half-way leaves it refusing to render ("no scene uploaded") instead of launching on freed buffers.
+	t->have_scene = false;
+	t->n_shapes = 0;
 	SRT_CUDA(t, t->shape_hdr.reserve(n_shapes));
 	SRT_CUDA(t, t->shape_a.reserve(n_shapes));
 	SRT_CUDA(t, t->shape_b.reserve(n_shapes));
@@ -430,7 +442,7 @@ int srt_render(srt_tracer *t, const srt_render_data *rd) {
 static size_t batch_cap(const srt::RenderParams &p) {
 	const size_t scratch_budget = (size_t)4 << 30;
 	const size_t fit = std::max<size_t>(1, scratch_budget / ((size_t)p.items_per_launch * sizeof(float4)));
-	return std::min<size_t>({(size_t)srt::MAX_BATCH, fit, (size_t)(0xfffffff0ull / p.items_per_launch)});
+	return std::min<size_t>({(size_t)srt::MAX_BATCH, fit, (size_t)(srt::MAX_ITEMS / p.items_per_launch)});
 }
 
 int srt_reserve_batch(srt_tracer *t, const srt_render_data *rd, size_t n) {
@@ -483,47 +495,85 @@ int srt_render_counted(srt_tracer *t, const srt_render_data *rd, srt_counters *c
 }
 
 int srt_resolve_device(srt_tracer *t, uint32_t num_steps) {
+	return srt_resolve_device_range(t, num_steps, 0, t ? (size_t)t->width * t->height : 0);
+}
+
+int srt_resolve_device_range(srt_tracer *t, uint32_t num_steps, size_t first_pixel, size_t count) {
 	SRT_BIND(t);
-	const int n = t->width * t->height;
-	srt::average_kernel<<<(n + 255) / 256, 256, 0, t->stream>>>(num_steps, t->canvas, t->output, n);
+	const size_t total = (size_t)t->width * t->height;
+	if (first_pixel > total || count > total - first_pixel) return fail(t, SRT_ERR_INVALID, "pixel range out of bounds");
+	if (count == 0) return SRT_OK;
+	const int n = (int)count;
+	srt::average_kernel<<<(n + 255) / 256, 256, 0, t->stream>>>(num_steps, t->canvas + first_pixel, t->output + first_pixel, n);
 	SRT_CUDA(t, cudaGetLastError());
+	return SRT_OK;
+}
+
+// The blocking read of the ARGB8 image, tracer.cpp:115.  The library never page-locks memory it does not own: the
+// copy goes through the handle's pinned staging buffer, in four chunks so that the host memcpy of chunk k overlaps
+// the DMA of chunk k + 1.  A caller who keeps ONE output buffer alive across frames (src/main.cpp:128) can opt in
+// to a direct copy with srt_pin_output.
+static int read_back(srt_tracer *t, uint8_t *dst) {
+	const size_t bytes = (size_t)t->width * t->height * 4;
+	const uint8_t *src = reinterpret_cast<const uint8_t *>(t->output);
+	if (t->registered_out && dst >= (uint8_t *)t->registered_out &&
+	    dst + bytes <= (uint8_t *)t->registered_out + t->registered_bytes) {
+		SRT_CUDA(t, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, t->stream));
+		SRT_CUDA(t, cudaStreamSynchronize(t->stream));
+		return SRT_OK;
+	}
+	const int chunks = bytes >= (1u << 20) ? 4 : 1;
+	const size_t step = ((bytes + chunks - 1) / chunks + 63) & ~(size_t)63;
+	for (int k = 0; k < chunks; ++k) {
+		const size_t off = std::min(bytes, k * step), len = std::min(bytes - off, step);
+		if (len) SRT_CUDA(t, cudaMemcpyAsync(t->pinned_out + off, src + off, len, cudaMemcpyDeviceToHost, t->stream));
+		SRT_CUDA(t, cudaEventRecord(t->chunk_ev[k], t->stream));
+	}
+	for (int k = 0; k < chunks; ++k) {
+		const size_t off = std::min(bytes, k * step), len = std::min(bytes - off, step);
+		SRT_CUDA(t, cudaEventSynchronize(t->chunk_ev[k]));
+		memcpy(dst + off, t->pinned_out + off, len);
+	}
 	return SRT_OK;
 }
 
 int srt_read_output(srt_tracer *t, uint8_t *argb_out) {
 	SRT_BIND(t);
 	if (!argb_out) return fail(t, SRT_ERR_INVALID, "output is null");
-	const size_t bytes = (size_t)t->width * t->height * 4;
-	SRT_CUDA(t, cudaMemcpyAsync(t->pinned_out, t->output, bytes, cudaMemcpyDeviceToHost, t->stream));
-	SRT_CUDA(t, cudaStreamSynchronize(t->stream));
-	memcpy(argb_out, t->pinned_out, bytes);
-	return SRT_OK;
+	return read_back(t, argb_out);
 }
 
 int srt_resolve(srt_tracer *t, uint32_t num_steps, uint8_t *argb_out) {
 	SRT_BIND(t);
 	if (!argb_out) return fail(t, SRT_ERR_INVALID, "output is null");
 	if (int rc = srt_resolve_device(t, num_steps)) return rc;
-	const size_t bytes = (size_t)t->width * t->height * 4;
-	// The blocking read of tracer.cpp:115.  The reference's caller hands in the same `pixels` vector every
-	// frame (src/main.cpp:128,290), so it is page-locked the second time it is seen and the copy lands in it directly;
-	// if that is refused (e.g. the memory is already registered) the handle's pinned staging buffer is used.
-	if (t->registered_out != argb_out) {
-		if (t->registered_out) cudaHostUnregister(t->registered_out);
-		t->registered_out = nullptr;
-		if (t->last_out == argb_out) {  // second frame into the same vector: worth page-locking
-			if (cudaHostRegister(argb_out, bytes, cudaHostRegisterDefault) == cudaSuccess) t->registered_out = argb_out;
-			else cudaGetLastError();
-		}
-		t->last_out = argb_out;
+	return read_back(t, argb_out);
+}
+
+int srt_pin_output(srt_tracer *t, void *buffer, size_t bytes) {
+	SRT_BIND(t);
+	if (!buffer || bytes == 0) return fail(t, SRT_ERR_INVALID, "srt_pin_output: null buffer");
+	if (int rc = srt_unpin_output(t)) return rc;
+	cudaError_t e = cudaHostRegister(buffer, bytes, cudaHostRegisterDefault);
+	if (e != cudaSuccess) {
+		cudaGetLastError();  // not sticky: the staging path keeps working
+		return fail(t, SRT_ERR_CUDA, "cudaHostRegister failed: %s", cudaGetErrorString(e));
 	}
-	if (t->registered_out == argb_out) {
-		SRT_CUDA(t, cudaMemcpyAsync(argb_out, t->output, bytes, cudaMemcpyDeviceToHost, t->stream));
-		SRT_CUDA(t, cudaStreamSynchronize(t->stream));
-	} else {
-		SRT_CUDA(t, cudaMemcpyAsync(t->pinned_out, t->output, bytes, cudaMemcpyDeviceToHost, t->stream));
-		SRT_CUDA(t, cudaStreamSynchronize(t->stream));
-		memcpy(argb_out, t->pinned_out, bytes);
+	t->registered_out = buffer;
+	t->registered_bytes = bytes;
+	return SRT_OK;
+}
+
+int srt_unpin_output(srt_tracer *t) {
+	SRT_BIND(t);
+	if (!t->registered_out) return SRT_OK;
+	SRT_CUDA(t, cudaStreamSynchronize(t->stream));
+	cudaError_t e = cudaHostUnregister(t->registered_out);
+	t->registered_out = nullptr;
+	t->registered_bytes = 0;
+	if (e != cudaSuccess) {
+		cudaGetLastError();
+		return fail(t, SRT_ERR_CUDA, "cudaHostUnregister failed: %s (was the buffer freed while pinned?)", cudaGetErrorString(e));
 	}
 	return SRT_OK;
 }
@@ -633,10 +683,17 @@ int srt_measure_fp32_peak(srt_tracer *t, double *tflops, double *sm_clock_mhz_es
 	SRT_BIND(t);
 	if (!tflops) return fail(t, SRT_ERR_INVALID, "tflops is null");
 	float *d = nullptr;
-	SRT_CUDA(t, cudaMalloc(&d, sizeof(float)));
-	cudaEvent_t e0, e1;
-	SRT_CUDA(t, cudaEventCreate(&e0));
-	SRT_CUDA(t, cudaEventCreate(&e1));
+	cudaEvent_t e0 = nullptr, e1 = nullptr;
+	auto cleanup = [&]() {
+		if (e0) cudaEventDestroy(e0);
+		if (e1) cudaEventDestroy(e1);
+		cudaFree(d);
+	};
+	if (cudaMalloc(&d, sizeof(float)) != cudaSuccess || cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) {
+		cleanup();
+		cudaGetLastError();
+		return fail(t, SRT_ERR_CUDA, "peak probe: allocation failed");
+	}
 	const int blocks = t->sm_count * 8, threads = 256, iters = 1 << 14;
 	double best = 0.0;
 	for (int rep = 0; rep < 6; ++rep) {
@@ -644,15 +701,16 @@ int srt_measure_fp32_peak(srt_tracer *t, double *tflops, double *sm_clock_mhz_es
 		srt::fma_peak_kernel<<<blocks, threads, 0, t->stream>>>(d, iters, 1.0000001f, 1e-9f);
 		cudaEventRecord(e1, t->stream);
 		cudaError_t e = cudaStreamSynchronize(t->stream);
-		if (e != cudaSuccess) return fail(t, SRT_ERR_CUDA, "peak kernel failed: %s", cudaGetErrorString(e));
+		if (e != cudaSuccess) {
+			cleanup();
+			return fail(t, SRT_ERR_CUDA, "peak kernel failed: %s", cudaGetErrorString(e));
+		}
 		float ms = 0.f;
 		cudaEventElapsedTime(&ms, e0, e1);
 		double fl = 2.0 * 16.0 * (double)iters * (double)blocks * threads;
 		if (rep > 0) best = std::max(best, fl / (ms * 1e-3) / 1e12);
 	}
-	cudaEventDestroy(e0);
-	cudaEventDestroy(e1);
-	cudaFree(d);
+	cleanup();
 	*tflops = best;
 	if (sm_clock_mhz_est) *sm_clock_mhz_est = best * 1e12 / (2.0 * 128.0 * t->sm_count) / 1e6;
 	return SRT_OK;

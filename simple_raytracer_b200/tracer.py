@@ -45,6 +45,8 @@ def load_library():
         "srt_render_batch": [vp, vp, sz],
         "srt_reserve_batch": [vp, vp, sz],
         "srt_resolve": [vp, u32, vp],
+        "srt_pin_output": [vp, vp, sz],
+        "srt_unpin_output": [vp],
         "srt_render_frame": [vp, vp, u32, vp],
         "srt_set_row_bands": [vp, i32, i32, i32],
         "srt_read_canvas": [vp, vp],
@@ -52,6 +54,7 @@ def load_library():
         "srt_canvas_device_ptr": [vp, pp, ctypes.POINTER(sz)],
         "srt_output_device_ptr": [vp, pp, ctypes.POINTER(sz)],
         "srt_resolve_device": [vp, u32],
+        "srt_resolve_device_range": [vp, u32, sz, sz],
         "srt_read_output": [vp, vp],
         "srt_stream": [vp, pp],
         "srt_synchronize": [vp],
@@ -131,6 +134,18 @@ class Tracer:
             raise ValueError("output must hold width*height*4 contiguous bytes (src/main.cpp:128)")
         self._check(self._lib.srt_render_frame(self._h, _p(self.options), int(ticks_stopped), _p(out)))
 
+    def pin_output(self, output):
+        """srt_pin_output: page-lock the ONE output buffer the caller hands to render() every frame
+        (src/main.cpp:128,290) so the read-back lands in it directly.  The caller keeps `output` alive until
+        unpin_output() / close(); the tracer holds a reference for as long as it is pinned."""
+        out = np.frombuffer(output, np.uint8) if not isinstance(output, np.ndarray) else output
+        self._check(self._lib.srt_pin_output(self._h, _p(out), out.nbytes))
+        self._pinned = out
+
+    def unpin_output(self):
+        self._check(self._lib.srt_unpin_output(self._h))
+        self._pinned = None
+
     # -- harness surface ------------------------------------------------------------------------
     def accumulate(self, render_data=None):
         """The `render` kernel launch alone (asynchronous): canvas += mean of num_samples paths."""
@@ -165,8 +180,11 @@ class Tracer:
     def resolve_device(self, num_steps):
         self._check(self._lib.srt_resolve_device(self._h, int(num_steps)))
 
-    def read_output(self):
-        out = np.empty((self.height, self.width, 4), np.uint8)
+    def resolve_device_range(self, num_steps, first_pixel, count):
+        self._check(self._lib.srt_resolve_device_range(self._h, int(num_steps), int(first_pixel), int(count)))
+
+    def read_output(self, output=None):
+        out = np.empty((self.height, self.width, 4), np.uint8) if output is None else output
         self._check(self._lib.srt_read_output(self._h, _p(out)))
         return out
 
@@ -227,8 +245,9 @@ class Tracer:
 
     def close(self):
         if getattr(self, "_h", None) and self._h.value:
-            self._lib.srt_destroy(self._h)
+            self._lib.srt_destroy(self._h)  # unpins before the buffer reference is dropped
             self._h = ctypes.c_void_p()
+        self._pinned = None
 
     def __del__(self):
         try:

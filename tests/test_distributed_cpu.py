@@ -16,9 +16,10 @@ class OracleRenderer:
     def __init__(self, scene, sky):
         import oracle
         self.o, self.scene, self.sky = oracle, scene, sky
+        self.width, self.height = scene.width, scene.height
         self.canvas = np.zeros((scene.height, scene.width, 4), np.float32)
         self.bands = None
-        self.output = None
+        self.output = np.zeros((scene.height, scene.width, 4), np.uint8)
 
     def clear_canvas(self):
         self.canvas[:] = 0
@@ -32,13 +33,19 @@ class OracleRenderer:
                       bands=self.bands, threads=1)
 
     def resolve_device(self, steps):
-        self.output = self.o.average(steps, self.canvas)
+        self.output[:] = self.o.average(steps, self.canvas)
+
+    def resolve_device_range(self, steps, first, count):
+        self.output.reshape(-1, 4)[first:first + count] = self.o.average(steps, self.canvas.reshape(-1, 4)[first:first + count])
 
     def resolve(self, steps):
         self.resolve_device(steps)
         return self.output
 
-    def read_output(self):
+    def read_output(self, output=None):
+        if output is not None:
+            output[:] = self.output
+            return output
         return self.output
 
 
@@ -67,7 +74,13 @@ def _worker(rank, world, port, q):
     canvas_s = r.canvas.copy()
     r2 = OracleRenderer(sc, sky)
     img_t = D.render_tile_sharded(r2, sc, rank, world, band_height=4, gather_fn=gather_fn)
-    q.put((rank, img_s, canvas_s if rank == 0 else None, img_t))
+    assert r2.bands is None  # the tracer is left rendering full frames
+    # the default exchange step: reduce-scatter, per-rank resolve of the own slice, gather of ARGB8 slices
+    r3 = OracleRenderer(sc, sky)
+    r3.set_row_bands(4, rank, world)  # sticky bands from an earlier tile-sharded run must not leak into this one
+    img_rs = D.render_sample_sharded(r3, sc, rank, world)
+    canvas_rs = D.gather_reduced_canvas(r3, rank, world)
+    q.put((rank, img_s, canvas_s if rank == 0 else None, img_t, img_rs, canvas_rs))
     dist.destroy_process_group()
 
 
@@ -100,8 +113,8 @@ def test_sample_and_tile_sharding_world2_gloo():
         p.start()
     results = {}
     for _ in range(2):
-        rank, img_s, canvas_s, img_t = q.get(timeout=150)
-        results[rank] = (img_s, canvas_s, img_t)
+        rank, img_s, canvas_s, img_t, img_rs, canvas_rs = q.get(timeout=150)
+        results[rank] = (img_s, canvas_s, img_t, img_rs, canvas_rs)
     for p in procs:
         p.join(30)
         assert p.exitcode == 0
@@ -113,10 +126,12 @@ def test_sample_and_tile_sharding_world2_gloo():
     for k in range(4):
         one.accumulate(sc.render_data(k))
     want = one.resolve(4)
-    img_s, canvas_s, img_t = results[0]
-    assert results[1][0] is None and results[1][2] is None
+    img_s, canvas_s, img_t, img_rs, canvas_rs = results[0]
+    assert results[1][0] is None and results[1][2] is None and results[1][3] is None
     # sample sharding: only the FP32 summation order differs (<= 1e-5 relative)
     assert np.allclose(canvas_s, one.canvas, rtol=1e-5, atol=1e-7)
     assert np.abs(img_s.astype(int) - want.astype(int)).max() <= 1
     # tile sharding: bit-identical by construction
     assert np.array_equal(img_t, want)
+    # reduce-scatter tail: the same sums as the reduce-to-root tail, slice by slice
+    assert np.array_equal(canvas_rs, canvas_s) and np.array_equal(img_rs, img_s)

@@ -64,6 +64,41 @@ def test_obj_round_trip(tmp_path, style):
     assert np.allclose(np.linalg.norm(got["v"]["normal"], axis=-1), 1.0, atol=1e-6)
 
 
+def test_loaders_reproduce_parser_cpp_byte_for_byte(tmp_path):
+    """The loaders' Triangle records equal what reference src/parser.cpp builds from the same files, byte for byte:
+    unnormalised STL facet normals kept, unnormalised OBJ `vn` normalised with glm::normalize's operations."""
+    from util import reference_parse
+    v, f = scenes.displaced_torus(16, 12, seed=4)
+    tris = scenes.mesh_triangles(v, f, None)
+    tris["v"]["normal"] *= np.float32(2.5)
+    write_stl(tmp_path / "a.stl", tris)
+    (_, count), got = tracer.load_stl_model(str(tmp_path / "a.stl"), np.zeros(0, TRIANGLE))
+    assert count == len(tris) and got.tobytes() == reference_parse("stl", v, None, f, tris).tobytes()
+    v, n, f = scenes.noisy_icosphere(2, seed=5)
+    n = (n * np.float32(0.3)).astype(np.float32)
+    write_obj(tmp_path / "a.obj", v, n, f)
+    (_, count), got = tracer.load_obj_model(str(tmp_path / "a.obj"), np.zeros(0, TRIANGLE))
+    assert count == len(f) and got.tobytes() == reference_parse("obj", v, n, f, None).tobytes()
+
+
+def test_stl_header_count_beyond_the_file_is_refused(tmp_path):
+    p = tmp_path / "huge.stl"
+    p.write_bytes(b"\0" * 80 + struct.pack("<I", 0xFFFFFFF0) + b"\0" * 100)
+    assert tracer.load_stl_model(str(p), np.zeros(0, TRIANGLE)) is None
+
+
+def test_model_bounds_enclose_the_unfused_device_transform():
+    """srt_model_bounds uses the device pre-transform's separately rounded products and sums (render.cl:114-120 order),
+    so the box is exactly the min / max of the world-space vertices the kernel intersects."""
+    v, n, f = scenes.noisy_icosphere(2, seed=6)
+    tris = scenes.mesh_triangles(v, f, n)
+    xf = (scenes.translate((1.3, -2.1, 3.7)) @ scenes.rotate_y(0.41) @ scenes.rotate_x(1.1) @ scenes.scale((2.3, 0.7, 0.51))).astype(np.float32)
+    rec = tracer.model_bounds(scenes.model(0, tris, 0, len(tris), xf), tris)
+    p = tris["v"]["pos"].reshape(-1, 3).astype(np.float32)
+    w = np.stack([((xf[r, 0] * p[:, 0] + xf[r, 1] * p[:, 1]) + xf[r, 2] * p[:, 2]) + xf[r, 3] * np.float32(1) for r in range(3)], 1)
+    assert np.array_equal(rec["model_bounding_min"], w.min(0)) and np.array_equal(rec["model_bounding_max"], w.max(0))
+
+
 def test_obj_negative_indices_quads_and_missing_normals(tmp_path):
     p = tmp_path / "q.obj"
     p.write_text("v 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nvn 0 0 2\nf -4//-1 -3//-1 -2//-1 -1//-1\nf 1 2 3\n")

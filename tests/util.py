@@ -102,3 +102,16 @@ def random_scene(seed, width=96, height=64, n_spheres=5, n_planes=3, n_boxes=2, 
     return scenes.Scene(f"random{seed}", width, height, 2, 7, 1, scenes._stack(shapes, scenes.SHAPE), tris,
                         scenes._stack(mats, scenes.MATERIAL),
                         scenes.camera_matrix((0, 0.2, 3.0), rng.uniform(-0.3, 0.3), rng.uniform(-0.2, 0.2)))
+
+
+def reference_parse(kind, v, n, f, tris):
+    """What reference src/parser.cpp produces from a mesh file written by test_mesh_io.write_stl / write_obj,
+    restated in numpy.  STL (:17-53): the facet normal is copied unnormalised to all three vertices, positions as
+    stored.  OBJ (:55-135): `vn` is glm::normalize'd at load (:83) = v * (1 / sqrt(x*x + y*y + z*z)) in float32."""
+    from simple_raytracer_b200 import scenes
+    if kind == "stl":
+        return tris
+    nn = np.asarray(n, np.float32)
+    d = (nn[:, 0] * nn[:, 0] + nn[:, 1] * nn[:, 1]) + nn[:, 2] * nn[:, 2]
+    inv = (np.float32(1.0) / np.sqrt(d)).astype(np.float32)
+    return scenes.mesh_triangles(v, f, (nn * inv[:, None]).astype(np.float32))
