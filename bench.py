@@ -223,7 +223,7 @@ def static_profile(cfg):
         return None
 
 
-def roofline_of(g, tr, scene, cfg, launch_rds, launch_ms, sm_mhz=None):
+def roofline_of(g, tr, scene, cfg, launch_rds, launch_ms, sm_mhz=None, profile=True):
     """Counted algorithmic flop of one launch (untimed instrumented pass, srt_render_counted) / its mean duration."""
     if g.peak_tf is None:
         g.peak_tf, g.est_mhz = tr.measure_fp32_peak()
@@ -242,7 +242,7 @@ def roofline_of(g, tr, scene, cfg, launch_rds, launch_ms, sm_mhz=None):
            "counted_launches": len(launch_rds),
            "Gtests_per_s": counters["tri_tests"] / len(launch_rds) / (launch_ms * 1e-3) / 1e9,
            "counters": counters, "traffic": None}
-    prof = static_profile(cfg)
+    prof = static_profile(cfg) if profile else None
     if prof:
         # `traffic`: ncu dram__bytes_read + dram__bytes_write of the render kernel + its accumulate epilogue per
         # reference launch, from the committed capture; `fma_pipe`: what the FMA pipe actually did (the algorithmic
@@ -291,10 +291,13 @@ def device_resident(g, tr, scene, rds, steps, warmup, resolve_steps, exchange=No
     return [a.elapsed_time(b) for a, b in evs], kernel_ms, kernel_launches
 
 
-def config_entry(g, cfg, with_cpu):
-    """One BASELINE config at full size on this GPU: device-resident throughput, roofline, CPU baseline."""
+def config_entry(g, cfg, with_cpu, accel="none"):
+    """One BASELINE config at full size on this GPU: device-resident throughput, roofline, CPU baseline.
+    accel = "bvh": the same workload through the OPTIONAL hierarchy (srt_set_accel) -- a labelled extension outside
+    the parity-graded path, reported separately: its flop figure counts the triangle tests it actually performs."""
     scene = scenes.CONFIGS[cfg]()
     tr = g.tracer(scene)
+    tr.set_accel(accel)
     rds = [scene.render_data(k) for k in range(scene.launches)]
     tr.reserve_batch(rds[0], len(rds))
     steps, warmup = (20, 3) if cfg == 1 else (1, 1)
@@ -305,10 +308,15 @@ def config_entry(g, cfg, with_cpu):
     step_ms, kernel_ms, n_launch = device_resident(g, tr, scene, rds, steps, 0, scene.launches)
     samples = scene.width * scene.height * scene.num_samples * scene.launches
     total_ms = sum(step_ms)
-    entry = {"config": workload_of(cfg, scene), "value": samples * steps / (total_ms * 1e-3) / 1e6, "unit": "Msamples/s",
+    entry = {"config": workload_of(cfg, scene), "accel": accel,
+             "value": samples * steps / (total_ms * 1e-3) / 1e6, "unit": "Msamples/s",
              "ms_per_step": total_ms / steps, "steps": steps, "timing": "CUDA events on the launching stream, device resident",
-             "roofline": roofline_of(g, tr, scene, cfg, rds[:1], kernel_ms / max(n_launch, 1))}
-    if with_cpu:
+             "roofline": roofline_of(g, tr, scene, cfg, rds[:1], kernel_ms / max(n_launch, 1), profile=accel == "none")}
+    if accel != "none":
+        entry["roofline"]["kernel"] = "srt::render_kernel<COUNT=false, MODE=BVH>"
+        entry["note"] = ("labelled extension outside the parity path (SURVEY 8f-4): tolerance-tested against the brute-force "
+                         "path (tests/test_gpu_bvh.py), not bit-tested against render.cl; flop counts its own triangle tests")
+    elif with_cpu:
         entry["cpu_baseline"] = cpu_baseline_dict(scene, g.sky, steps=1, budget_s=3.0, window=CPU_WINDOWS.get(cfg))
     tr.close()
     return entry
@@ -482,6 +490,7 @@ def main():
     if not args.no_extras:
         if world == 1:
             configs = [config_entry(g, c, not args.no_cpu_baseline) for c in (1, 3, 4, 5) if c != args.config]
+            configs += [config_entry(g, c, False, accel="bvh") for c in (3, 5)]
         else:
             strong = [strong_entry(g, 4, "sample"), strong_entry(g, 5, "tile")]
             if rank == 0:

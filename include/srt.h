@@ -150,6 +150,16 @@ int srt_render_frame(srt_tracer *t, const srt_render_data *rd, uint32_t ticks_st
  * every sample is bit-identical to a full-frame launch.  band_count <= 1 renders all rows. */
 int srt_set_row_bands(srt_tracer *t, int band_height, int band_index, int band_count);
 
+/* OPTIONAL acceleration structure -- a labelled extension OUTSIDE the parity-graded path.  The
+ * reference brute-forces every triangle of a model whose box the ray enters (render.cl:324) and lists a BVH first among
+ * its future plans (README.md:41).  SRT_ACCEL_NONE (the default) is that brute-force path, bit-exact with render.cl.
+ * SRT_ACCEL_BVH builds, at this call and at every later srt_upload_scene, a bounding-volume hierarchy over each model
+ * of more than 32 triangles and traverses it instead: same exact test on the same operands, closest hit, equal t to
+ * the lowest triangle index -- but only triangles whose boxes the ray enters are tested, so results are equal to the
+ * brute-force path only up to its rounding-noise hits on far-away edge-on triangles (tolerance-tested, not bit-tested). */
+enum { SRT_ACCEL_NONE = 0, SRT_ACCEL_BVH = 1 };
+int srt_set_accel(srt_tracer *t, int accel);
+
 /* Harness / test entry points (no reference counterpart). */
 int srt_read_canvas(srt_tracer *t, float *rgba_out);               /* width*height*4 floats; synchronises */
 int srt_write_canvas(srt_tracer *t, const float *rgba_in);         /* restore an accumulation (checkpoint/resume) */

@@ -7,8 +7,9 @@
 // boost.compute members are replaced by one srt_tracer handle.  Errors surface as std::runtime_error
 // where the reference throws boost::compute::opencl_error.
 //
-// Neither glm nor the OpenCL `cl_*` typedefs are required: the records are the plain-C structs of srt.h,
-// byte-identical to the reference's `Shape` / `Triangle` / `Material` (static_asserted in srt_api.cu).
+// Neither glm nor the OpenCL `cl_*` typedefs are required: `Shape` / `Triangle` / `Material` (scene.hpp) derive from
+// the plain-C records of srt.h, byte-identical to the reference's structs (static_asserted in srt_api.cu), and carry
+// the reference's constructors, `Model` / `Box` helpers and the `load_*_model` / `save_ppm` functions.
 // A build that still has glm keeps using its own shape.hpp/material.hpp types and passes
 // reinterpret_cast pointers -- the layouts are the same.
 #pragma once
@@ -18,13 +19,10 @@
 #include <string>
 #include <vector>
 
+#include "scene.hpp"
 #include "srt.h"
 
 namespace srt_facade {
-
-using Shape = srt_shape;
-using Triangle = srt_triangle;
-using Material = srt_material;
 
 class Tracer {
   public:

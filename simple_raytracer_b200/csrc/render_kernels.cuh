@@ -52,6 +52,10 @@ struct DevScene {
 	const float4 *model_xf;   // 4 per shape slot: model matrix columns      (cold)
 	const float4 *materials;  // 4 per material: the reference's 64-byte record as 4 x float4
 	const float4 *sky;        // RGBA f32 texels, row 0 = v 0
+	// optional acceleration structure (srt_set_accel(SRT_ACCEL_BVH); null otherwise): bvh_build.hpp
+	const float4 *bvh_nodes;  // 4 per node: {lo0, c0} {hi0, n0} {lo1, c1} {hi1, n1}
+	const int *bvh_order;     // leaf slots -> SoA triangle index
+	const int *bvh_root;      // per shape slot: entry node of the model's hierarchy, -1 = none (brute force)
 	int sky_w, sky_h;
 	float sun_focus, sun_intensity;
 	float sun_color[3];
@@ -188,6 +192,86 @@ __device__ __forceinline__ void test_triangle(const float4 v0, const float4 e1, 
 	if (tri_filter(v0, e1, e2, o, d)) tri_exact(v0, e1, e2, o, d, shape, tri, hit);
 }
 
+// ---- optional BVH traversal (a labelled extension outside the parity path: srt_set_accel, bvh_build.hpp) ----------
+// Same exact test, same operands (tri_hot) as the brute-force loop; only the SET of triangles tested differs: those
+// in leaves whose (padded) boxes the ray enters no farther than the closest hit so far.  Closest hit wins; on equal t
+// the lowest triangle index of THIS model wins and a hit of an earlier shape is kept (render.cl:332 with its strict
+// `<`, evaluated in triangle order) -- so traversal order does not matter.
+constexpr int BVH_STACK = 48;
+__device__ __forceinline__ void tri_exact_tie(const float4 v0, const float4 e1, const float4 e2, vec3 o, vec3 d, int shape,
+                                              int tri, Hit &hit) {
+	vec3 h = cross(d, xyz(e2));
+	float det = dot(xyz(e1), h);
+	float f = rcp_(det);
+	vec3 s = o - xyz(v0);
+	float u = f * dot(s, h);
+	if (u < 0.0f || u > 1.0f) return;
+	vec3 q = cross(s, xyz(e1));
+	float v = f * dot(d, q);
+	if (v < 0.0f || u + v > 1.0f) return;
+	float t = f * dot(xyz(e2), q);
+	if (t > 0.0f && (t < hit.t || (t == hit.t && hit.shape == shape && tri < hit.tri))) {
+		hit.t = t;
+		hit.shape = shape;
+		hit.tri = tri;
+	}
+}
+// entry distance of the ray into a box, or +inf when it misses it or enters beyond tmax.  fminf / fmaxf drop NaNs
+// (0 * inf on a slab boundary), and the exit distance is widened by 4 ulp: a box is never culled by rounding.
+__device__ __forceinline__ float bvh_slab(const float4 lo, const float4 hi, vec3 o, vec3 inv, float tmax) {
+	const float x0 = (lo.x - o.x) * inv.x, x1 = (hi.x - o.x) * inv.x;
+	const float y0 = (lo.y - o.y) * inv.y, y1 = (hi.y - o.y) * inv.y;
+	const float z0 = (lo.z - o.z) * inv.z, z1 = (hi.z - o.z) * inv.z;
+	const float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.0f));
+	const float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), tmax)) * 1.0000005f;
+	return tn <= tf ? tn : __int_as_float(0x7f800000);
+}
+template <bool COUNT>
+__device__ __forceinline__ void bvh_leaf(const DevScene &sc, int first, int n, vec3 o, vec3 d, int shape, Hit &hit,
+                                         Counters &cnt) {
+	for (int k = 0; k < n; ++k) {
+		const int tri = __ldg(&sc.bvh_order[first + k]);
+		const float4 *tp = sc.tri_hot + 3 * (size_t)tri;
+		if (COUNT) cnt.tri_tests += 1;
+		tri_exact_tie(__ldg(tp), __ldg(tp + 1), __ldg(tp + 2), o, d, shape, tri, hit);
+	}
+}
+template <bool COUNT>
+__device__ __noinline__ void bvh_traverse(const DevScene &sc, int root, vec3 o, vec3 d, vec3 inv, int shape, Hit &hit,
+                                          Counters &cnt) {
+	const float INF = __int_as_float(0x7f800000);
+	int stack[BVH_STACK];
+	int sp = 0;
+	int node = root;
+	for (;;) {
+		const float4 a = __ldg(&sc.bvh_nodes[4 * (size_t)node + 0]), b = __ldg(&sc.bvh_nodes[4 * (size_t)node + 1]);
+		const float4 c = __ldg(&sc.bvh_nodes[4 * (size_t)node + 2]), e = __ldg(&sc.bvh_nodes[4 * (size_t)node + 3]);
+		const int c0 = __float_as_int(a.w), n0 = __float_as_int(b.w), c1 = __float_as_int(c.w), n1 = __float_as_int(e.w);
+		float t0 = n0 < 0 ? INF : bvh_slab(a, b, o, inv, hit.t);
+		float t1 = n1 < 0 ? INF : bvh_slab(c, e, o, inv, hit.t);
+		if (t0 < INF && n0 > 0) {  // leaves are tested on the spot
+			bvh_leaf<COUNT>(sc, c0, n0, o, d, shape, hit, cnt);
+			t0 = INF;
+		}
+		if (t1 < INF && n1 > 0) {
+			if (t1 <= hit.t) bvh_leaf<COUNT>(sc, c1, n1, o, d, shape, hit, cnt);
+			t1 = INF;
+		}
+		if (t0 < INF && t1 < INF) {  // two inner children: nearer first, the other waits on the stack
+			const bool first0 = t0 <= t1;
+			if (sp < BVH_STACK) stack[sp++] = first0 ? c1 : c0;
+			node = first0 ? c0 : c1;
+		} else if (t0 < INF) {
+			node = c0;
+		} else if (t1 < INF) {
+			node = c1;
+		} else {
+			if (sp == 0) return;
+			node = stack[--sp];
+		}
+	}
+}
+
 // ---- shape scan ------------------------------------------------------------------------------
 // reference closest_intersection, render.cl:293-378, as a resumable scan.  Shapes are visited in
 // array order starting at `cursor`, and a hit replaces the current one only if strictly closer
@@ -197,7 +281,7 @@ __device__ __forceinline__ void test_triangle(const float4 v0, const float4 e1, 
 // resumes at index + 1.  Returns -1 when the scan reached the end of the list.
 // Normal / position of the winner are reconstructed afterwards (finish_hit) instead of at every
 // improvement; only the last improvement is observable.
-template <bool COUNT, bool PARK, bool MODELS = true>
+template <bool COUNT, bool PARK, bool MODELS = true, bool BVH = false>
 __device__ __forceinline__ int scan_shapes(const DevScene &sc, vec3 o, vec3 d, vec3 inv, int cursor, Hit &hit,
                                            Counters &cnt) {
 	for (int i = cursor; i < sc.num_shapes; ++i) {
@@ -246,6 +330,14 @@ __device__ __forceinline__ int scan_shapes(const DevScene &sc, vec3 o, vec3 d, v
 				tmax = min_(tmax, max_(t1, t2));
 			}
 			if (tmin < tmax) {
+				if (BVH) {  // labelled extension: only the triangles of the leaves the ray enters are tested
+					const int root = __ldg(&sc.bvh_root[i]);
+					if (root >= 0) {
+						if (COUNT) cnt.aabb_pass += 1;
+						bvh_traverse<COUNT>(sc, root, o, d, inv, i, hit, cnt);
+						continue;
+					}
+				}
 				if (COUNT) {
 					cnt.aabb_pass += 1;
 					cnt.tri_tests += (unsigned)hdr.w;
@@ -409,6 +501,9 @@ __device__ __forceinline__ void scatter(const DevScene &sc, int material, vec3 p
 #endif
 #ifndef SRT_MIN_BLOCKS_ANALYTIC
 #define SRT_MIN_BLOCKS_ANALYTIC 8
+#endif
+#ifndef SRT_MIN_BLOCKS_BVH
+#define SRT_MIN_BLOCKS_BVH 6
 #endif
 constexpr int RENDER_THREADS = SRT_RENDER_THREADS;
 
@@ -692,9 +787,11 @@ constexpr int BIG_SKYQ_BYTES = SRT_BIG_SKYQ ? (SRT_RENDER_THREADS / 32) * SKYQ_W
 // MODE_SMALL_MODELS when every model is small enough to be intersected inline during the scan (no
 // parking, no shared memory), MODE_BIG_MODELS for the full machine.  The first two need fewer registers,
 // i.e. more resident warps for the latency-bound analytic path.
-enum { MODE_ANALYTIC = 0, MODE_SMALL_MODELS = 1, MODE_BIG_MODELS = 2 };
+// MODE_BVH (srt_set_accel(SRT_ACCEL_BVH), NOT the parity path) is the SMALL_MODELS machine with big models traversed
+// through their hierarchy inside the scan.
+enum { MODE_ANALYTIC = 0, MODE_SMALL_MODELS = 1, MODE_BIG_MODELS = 2, MODE_BVH = 3 };
 template <bool COUNT, int MODE>
-__global__ void __launch_bounds__(RENDER_THREADS, MODE == MODE_BIG_MODELS ? SRT_MIN_BLOCKS : SRT_MIN_BLOCKS_ANALYTIC)
+__global__ void __launch_bounds__(RENDER_THREADS, MODE == MODE_BIG_MODELS ? SRT_MIN_BLOCKS : (MODE == MODE_BVH ? SRT_MIN_BLOCKS_BVH : SRT_MIN_BLOCKS_ANALYTIC))
 render_kernel(const __grid_constant__ RenderParams p, const __grid_constant__ DevScene sc,
               float4 *__restrict__ scratch, unsigned long long *__restrict__ cursor, Counters *__restrict__ counters) {
 	const unsigned FULL = 0xffffffffu;
@@ -849,7 +946,7 @@ render_kernel(const __grid_constant__ RenderParams p, const __grid_constant__ De
 				if (MODELS) inv = mk(rcp_(d.x), rcp_(d.y), rcp_(d.z));
 				scan_at = 0;
 			}
-			park = scan_shapes<COUNT, PHASES, MODELS>(sc, o, d, inv, scan_at, hit, cnt);
+			park = scan_shapes<COUNT, PHASES, MODELS, MODE == MODE_BVH>(sc, o, d, inv, scan_at, hit, cnt);
 
 			if (park < 0) {  // scan complete: shade this bounce, :404-468
 				scan_at = -1;
@@ -999,6 +1096,7 @@ average_kernel(uint32_t num_steps, const float4 *__restrict__ canvas, uchar4 *__
 }
 
 // ---- debug: primary hit of every pixel's sample-0 camera ray -----------------------------------
+template <bool BVH>
 __global__ void __launch_bounds__(256)
 primary_kernel(const __grid_constant__ RenderParams p, const __grid_constant__ DevScene sc,
                int *__restrict__ shape_idx, float *__restrict__ t_out) {
@@ -1011,7 +1109,7 @@ primary_kernel(const __grid_constant__ RenderParams p, const __grid_constant__ D
 	Counters cnt = {0, 0, 0, 0, 0, 0};
 	Hit hit = {__int_as_float(0x7f800000), -1, -1};
 	vec3 inv = mk(rcp_(d.x), rcp_(d.y), rcp_(d.z));
-	scan_shapes<false, false>(sc, o, d, inv, 0, hit, cnt);
+	scan_shapes<false, false, true, BVH>(sc, o, d, inv, 0, hit, cnt);
 	shape_idx[id] = hit.shape;
 	t_out[id] = hit.t;
 }

@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "../../include/srt.h"
+#include "bvh_build.hpp"
 #include "render_kernels.cuh"
 
 static_assert(sizeof(srt_material) == 64 && offsetof(srt_material, color) == 32 && offsetof(srt_material, emission) == 48, "material");
@@ -81,13 +82,20 @@ struct srt_tracer {
 	DevBuf<float> model_k;   // per shape slot
 	DevBuf<float4> scratch;  // one float4 per (pixel, sample) of a launch
 	DevBuf<srt::ModelSpan> spans;
+	// optional BVH (srt_set_accel): a labelled extension outside the parity path
+	int accel = SRT_ACCEL_NONE;
+	bool bvh_ready = false;
+	int bvh_depth = 0;
+	DevBuf<float4> bvh_nodes;
+	DevBuf<int> bvh_order, bvh_root;
+	std::vector<int4> host_hdr;  // the shape headers of the uploaded scene (the BVH builder walks the models)
 	size_t n_shapes = 0, n_materials = 0, n_soa_tris = 0;
 	bool has_models = false, has_big_models = false;
 	srt_scene_data scene_data{};
 	bool have_scene = false;
 
 	int band_h = 1, band_i = 0, band_n = 1;
-	int render_grid[2][3] = {{0, 0, 0}, {0, 0, 0}};  // [counted][mode]
+	int render_grid[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};  // [counted][mode]
 
 	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing;  // kernel launches since last query
 	uint64_t timed_launches = 0;                               // reference launches they cover (batches count each)
@@ -134,6 +142,10 @@ srt::DevScene dev_scene(const srt_tracer *t) {
 	s.model_xf = t->model_xf.ptr;
 	s.materials = t->materials.ptr;
 	s.sky = t->sky;
+	const bool bvh = t->accel == SRT_ACCEL_BVH && t->bvh_ready;
+	s.bvh_nodes = bvh ? t->bvh_nodes.ptr : nullptr;
+	s.bvh_order = bvh ? t->bvh_order.ptr : nullptr;
+	s.bvh_root = bvh ? t->bvh_root.ptr : nullptr;
 	s.sky_w = t->sky_w;
 	s.sky_h = t->sky_h;
 	const srt_scene_data &sd = t->scene_data;
@@ -225,6 +237,7 @@ int launch_render_impl(srt_tracer *t, const srt::RenderParams &p) {
 template <bool COUNT>
 int launch_params(srt_tracer *t, const srt::RenderParams &p) {
 	if (!t->has_models) return launch_render_impl<COUNT, srt::MODE_ANALYTIC>(t, p);
+	if (t->accel == SRT_ACCEL_BVH && t->bvh_ready && t->has_big_models) return launch_render_impl<COUNT, srt::MODE_BVH>(t, p);
 	if (!t->has_big_models) return launch_render_impl<COUNT, srt::MODE_SMALL_MODELS>(t, p);
 	return launch_render_impl<COUNT, srt::MODE_BIG_MODELS>(t, p);
 }
@@ -235,6 +248,40 @@ int launch_render(srt_tracer *t, const srt_render_data *rd) {
 	if (int rc = make_params(t, rd, p)) return rc;
 	if (p.num_bounces == 0 || p.total_items == 0) return SRT_OK;  // render.cl:403: zero bounces add zero radiance
 	return launch_params<COUNT>(t, p);
+}
+
+// (Re)build the optional hierarchy over the uploaded scene: one per model of more than INLINE_MODEL_TRIS triangles,
+// over the world-space triangles exactly as the kernel intersects them (tri_hot, read back from the device).
+int build_bvh(srt_tracer *t) {
+	t->bvh_ready = false;
+	const size_t n_shapes = t->host_hdr.size();
+	std::vector<int> roots(n_shapes, -1);
+	std::vector<srt_bvh::Node> nodes;
+	std::vector<int32_t> order;
+	int depth = 0;
+	try {
+		std::vector<float> hot(12 * t->n_soa_tris);
+		if (t->n_soa_tris)
+			SRT_CUDA(t, cudaMemcpy(hot.data(), t->tri_hot.ptr, hot.size() * sizeof(float), cudaMemcpyDeviceToHost));
+		for (size_t i = 0; i < n_shapes; ++i) {
+			const int4 h = t->host_hdr[i];
+			if (h.x != SRT_SHAPE_MODEL || h.w <= srt::INLINE_MODEL_TRIS) continue;
+			roots[i] = (int)nodes.size();
+			depth = std::max(depth, srt_bvh::build(hot.data(), h.z, h.w, nodes, order));
+		}
+	} catch (const std::exception &) {
+		return fail(t, SRT_ERR_INVALID, "out of host memory while building the BVH");
+	}
+	if (depth > srt::BVH_STACK) return fail(t, SRT_ERR_INVALID, "BVH depth %d exceeds the traversal stack (%d)", depth, srt::BVH_STACK);
+	SRT_CUDA(t, t->bvh_nodes.reserve(4 * nodes.size()));
+	SRT_CUDA(t, t->bvh_order.reserve(order.size()));
+	SRT_CUDA(t, t->bvh_root.reserve(n_shapes));
+	if (!nodes.empty()) SRT_CUDA(t, cudaMemcpy(t->bvh_nodes.ptr, nodes.data(), nodes.size() * sizeof(srt_bvh::Node), cudaMemcpyHostToDevice));
+	if (!order.empty()) SRT_CUDA(t, cudaMemcpy(t->bvh_order.ptr, order.data(), order.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+	if (n_shapes) SRT_CUDA(t, cudaMemcpy(t->bvh_root.ptr, roots.data(), n_shapes * sizeof(int), cudaMemcpyHostToDevice));
+	t->bvh_depth = depth;
+	t->bvh_ready = true;
+	return SRT_OK;
 }
 
 // true when two launches differ in nothing the kernel reads except `time` (`tick` is unused, render.cl:91)
@@ -325,6 +372,7 @@ int srt_destroy(srt_tracer *t) {
 	cudaFree(t->counters);
 	cudaFree(t->sky);
 	t->shape_hdr.release(), t->shape_a.release(), t->shape_b.release(), t->model_xf.release(), t->materials.release();
+	t->bvh_nodes.release(), t->bvh_order.release(), t->bvh_root.release();
 	t->tri_aos.release(), t->tri_hot.release(), t->tri_flt.release(), t->model_k.release(), t->tri_n.release(), t->spans.release(), t->scratch.release();
 	if (t->stream) cudaStreamDestroy(t->stream);
 	delete t;
@@ -423,7 +471,21 @@ int srt_upload_scene(srt_tracer *t, const srt_shape *shapes, size_t n_shapes, co
 	t->has_models = soa > 0 || std::any_of(hdr.begin(), hdr.end(), [](const int4 &h) { return h.x == SRT_SHAPE_MODEL; });
 	t->scene_data = *scene_data;
 	t->scene_data.num_shapes = (int)n_shapes;  // tracer.cpp:94
+	t->host_hdr = hdr;
+	t->bvh_ready = false;
 	t->have_scene = true;
+	if (t->accel == SRT_ACCEL_BVH) return build_bvh(t);
+	return SRT_OK;
+}
+
+int srt_set_accel(srt_tracer *t, int accel) {
+	SRT_BIND(t);
+	if (accel != SRT_ACCEL_NONE && accel != SRT_ACCEL_BVH) return fail(t, SRT_ERR_INVALID, "unknown acceleration mode %d", accel);
+	t->accel = accel;
+	if (accel == SRT_ACCEL_BVH && t->have_scene && !t->bvh_ready) {
+		SRT_CUDA(t, cudaStreamSynchronize(t->stream));
+		return build_bvh(t);
+	}
 	return SRT_OK;
 }
 
@@ -649,7 +711,10 @@ int srt_debug_primary(srt_tracer *t, const srt_render_data *rd, int32_t *shape_i
 		cudaFree(d_idx);
 		return fail(t, SRT_ERR_CUDA, "cudaMalloc failed");
 	}
-	srt::primary_kernel<<<(n + 255) / 256, 256, 0, t->stream>>>(p, dev_scene(t), d_idx, d_t);
+	if (t->accel == SRT_ACCEL_BVH && t->bvh_ready)
+		srt::primary_kernel<true><<<(n + 255) / 256, 256, 0, t->stream>>>(p, dev_scene(t), d_idx, d_t);
+	else
+		srt::primary_kernel<false><<<(n + 255) / 256, 256, 0, t->stream>>>(p, dev_scene(t), d_idx, d_t);
 	cudaError_t e = cudaGetLastError();
 	if (e == cudaSuccess) e = cudaMemcpyAsync(shape_idx, d_idx, n * sizeof(int), cudaMemcpyDeviceToHost, t->stream);
 	if (e == cudaSuccess) e = cudaMemcpyAsync(t_out, d_t, n * sizeof(float), cudaMemcpyDeviceToHost, t->stream);

@@ -123,6 +123,37 @@ def cube_triangles():
     return triangles_from(np.array(pos), np.array(nrm))
 
 
+def reference_cube_triangles():
+    """The same 12 triangles in the order Box::create_triangle emits them (/root/reference/src/shape.cpp:91-119;
+    C++ twin: include/scene.hpp Box::create_triangle): corner i at (i&4 ? +1 : -1, i&1 ? +1 : -1, i&2 ? -1 : +1)."""
+    faces = "120362746504602357132376754510640315"
+    corner = [np.array([1 if i & 4 else -1, 1 if i & 1 else -1, -1 if i & 2 else 1], F) for i in range(8)]
+    pos, nrm = [], []
+    for k in range(12):
+        v1, v2, v3 = (corner[int(c)] for c in faces[3 * k:3 * k + 3])
+        a, b = v2 - v1, v3 - v1
+        n = np.array([a[1] * b[2] - b[1] * a[2], a[2] * b[0] - b[2] * a[0], a[0] * b[1] - b[0] * a[1]], F)
+        if not (v1[0] * n[0] + v1[1] * n[1] + v1[2] * n[2]) > 0:
+            n = -n
+        n = n * (F(1) / np.sqrt(F(n[0] * n[0] + n[1] * n[1] + n[2] * n[2])))
+        pos.append([v1, v2, v3])
+        nrm.append([n, n, n])
+    return triangles_from(np.array(pos, F), np.array(nrm, F))
+
+
+def box_model(mat, position, size=2.0):
+    """Shape{mat, Box::model(position, size)}, /root/reference/src/shape.cpp:76-89: transform = translate(position)
+    only, AABB = position -+ size / 2, triangles [0, 12)."""
+    s = np.zeros((), SHAPE)
+    s["type"], s["material"] = SHAPE_MODEL, mat
+    s["model_triangle_index"], s["model_num_triangles"] = 0, 12
+    p = np.asarray(position, F)
+    half = np.broadcast_to(np.asarray(size, F), (3,)) * F(0.5)
+    s["model_bounding_min"], s["model_bounding_max"] = p - half, p + half
+    s["model_transform"] = to_columns(translate(p))
+    return s
+
+
 def icosphere(subdiv):
     t = (1.0 + 5.0 ** 0.5) / 2.0
     v = np.array([[-1, t, 0], [1, t, 0], [-1, -t, 0], [1, -t, 0], [0, -1, t], [0, 1, t],

@@ -49,6 +49,7 @@ def load_library():
         "srt_unpin_output": [vp],
         "srt_render_frame": [vp, vp, u32, vp],
         "srt_set_row_bands": [vp, i32, i32, i32],
+        "srt_set_accel": [vp, i32],
         "srt_read_canvas": [vp, vp],
         "srt_write_canvas": [vp, vp],
         "srt_canvas_device_ptr": [vp, pp, ctypes.POINTER(sz)],
@@ -190,6 +191,11 @@ class Tracer:
 
     def set_row_bands(self, band_height, band_index, band_count):
         self._check(self._lib.srt_set_row_bands(self._h, band_height, band_index, band_count))
+
+    def set_accel(self, accel):
+        """srt_set_accel: "none" (default: the reference's brute-force triangle loop, bit-exact) or "bvh" (labelled
+        extension outside the parity path)."""
+        self._check(self._lib.srt_set_accel(self._h, {"none": 0, "bvh": 1}[accel]))
 
     def read_canvas(self):
         out = np.empty((self.height, self.width, 4), np.float32)

@@ -33,14 +33,69 @@ def test_c_header_is_plain_c(tmp_path):
                            "-o", str(tmp_path / "t.o")])
 
 
-@pytest.mark.gpu
-def test_headless_harness_matches_python_path_and_oracle(tmp_path, oracle_lib):
+def _mirror_scene(w, h, frames, mesh_tris=None):
+    """The scene examples/headless.cpp builds with the C++ helpers, rebuilt with the Python ones."""
     from simple_raytracer_b200 import scenes
+    from simple_raytracer_b200.records import concat_records
+    F = np.float32
+    mats = [scenes.material((0.8, 0.8, 0.8)),
+            scenes.material((1, 1, 1), smoothness=1.0, transmittance=1.0, refraction_index=1.5),
+            scenes.material((0.25, 0.4, 0.95), smoothness=0.95, metallic=1.0),
+            scenes.material((1, 0.2, 0.15), emission=(1, 0.15, 0.1), emission_strength=5.0)]
+    tris = scenes.reference_cube_triangles()
+    shapes = [scenes.plane(0, (0, -2, 0), (0, 1, 0)), scenes.sphere(0, (-3.2, 0, -3), 2.0),
+              scenes.sphere(1, (0.6, -0.8, -0.5), 1.2), scenes.sphere(2, (3.4, -0.6, -2.6), 1.4),
+              scenes.sphere(3, (-0.4, -1.3, -4.6), 0.7), scenes.box_model(2, (1.5, -1.0, 1.0), 2.0)]
+    if mesh_tris is not None:
+        tris = concat_records(scenes.TRIANGLE, tris, mesh_tris)
+        shapes.append(scenes.model(0, tris, 12, len(mesh_tris)))
+    sc = scenes.Scene("headless", w, h, 2, 10, frames, scenes._stack(shapes, scenes.SHAPE), tris,
+                      scenes._stack(mats, scenes.MATERIAL), scenes.camera_matrix((0, 0.5, 5.5)))
+    sc.scene_data["sun_color"] = [1.0, 1.0, F(0xD3) / F(255.0)]
+    inv = F(1.0) / np.sqrt(F(2.0))
+    sc.scene_data["sun_direction"] = [inv, -inv, 0.0]
+    return sc
+
+
+def _mesh_file(tmp_path):
+    from simple_raytracer_b200 import scenes
+    from test_mesh_io import write_stl
+    v, f = scenes.displaced_torus(20, 12, seed=31, R=0.9, r=0.35)
+    v = (v + np.array([-1.2, -0.6, 1.8], np.float32)).astype(np.float32)
+    tris = scenes.mesh_triangles(v, f, None)
+    path = tmp_path / "torus.stl"
+    write_stl(path, tris)
+    return path, tris
+
+
+def test_cpp_scene_helpers_build_the_same_bytes_as_the_python_mirror(tmp_path):
+    """include/scene.hpp (Material / Sphere / Plane / Model / Box / Shape constructors, load_stl_model) against
+    records.py / scenes.py: the C++ harness dumps its three scene vectors, which must equal the Python-built scene byte
+    for byte -- including Box::create_triangle's triangle order and Model's bounding box.  No GPU involved."""
+    build_harness()
+    path, mesh = _mesh_file(tmp_path)
+    prefix = str(tmp_path / "scene")
+    subprocess.check_call([EXE, str(tmp_path / "unused.ppm"), "64", "48", "1", str(path)],
+                          env=dict(os.environ, SRT_DUMP_SCENE=prefix))
+    sc = _mirror_scene(64, 48, 1, mesh)
+    assert open(prefix + ".materials", "rb").read() == sc.materials.tobytes()
+    assert open(prefix + ".triangles", "rb").read() == sc.triangles.tobytes()
+    assert open(prefix + ".shapes", "rb").read() == sc.shapes.tobytes()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("with_mesh", [False, True])
+def test_headless_harness_matches_python_path_and_oracle(tmp_path, oracle_lib, with_mesh):
     from simple_raytracer_b200.tracer import Tracer
     build_harness()
     w, h, frames = 200, 120, 3
     out = tmp_path / "o.ppm"
-    subprocess.check_call([EXE, str(out), str(w), str(h), str(frames)])
+    mesh = None
+    args = [EXE, str(out), str(w), str(h), str(frames)]
+    if with_mesh:  # "Add model" through load_stl_model + Model(triangles, first, count)
+        path, mesh = _mesh_file(tmp_path)
+        args.append(str(path))
+    subprocess.check_call(args)
     data = out.read_bytes()
     header = f"P6 {w} {h} 255\n".encode()
     assert data.startswith(header)
@@ -51,18 +106,7 @@ def test_headless_harness_matches_python_path_and_oracle(tmp_path, oracle_lib):
     sky = np.ones((32, 64, 4), F)
     v = ((np.arange(32, dtype=F) + F(0.5)) / F(32))[:, None]
     sky[..., 0], sky[..., 1], sky[..., 2] = F(0.25) + F(0.3) * v, F(0.35) + F(0.35) * v, F(0.5) + F(0.45) * v
-    mats = [scenes.material((0.8, 0.8, 0.8)),
-            scenes.material((1, 1, 1), smoothness=1.0, transmittance=1.0, refraction_index=1.5),
-            scenes.material((0.25, 0.4, 0.95), smoothness=0.95, metallic=1.0),
-            scenes.material((1, 0.2, 0.15), emission=(1, 0.15, 0.1), emission_strength=5.0)]
-    shapes = [scenes.plane(0, (0, -2, 0), (0, 1, 0)), scenes.sphere(0, (-3.2, 0, -3), 2.0),
-              scenes.sphere(1, (0.6, -0.8, -0.5), 1.2), scenes.sphere(2, (3.4, -0.6, -2.6), 1.4),
-              scenes.sphere(3, (-0.4, -1.3, -4.6), 0.7)]
-    sc = scenes.Scene("headless", w, h, 2, 10, frames, scenes._stack(shapes, scenes.SHAPE), np.zeros(0, scenes.TRIANGLE),
-                      scenes._stack(mats, scenes.MATERIAL), scenes.camera_matrix((0, 0.5, 5.5)))
-    sc.scene_data["sun_color"] = [1.0, 1.0, F(0xD3) / F(255.0)]
-    inv = F(1.0) / np.sqrt(F(2.0))
-    sc.scene_data["sun_direction"] = [inv, -inv, 0.0]
+    sc = _mirror_scene(w, h, frames, mesh)
     tr = Tracer(w, h, sky)
     tr.scene_data[:] = sc.scene_data
     tr.clear_canvas()

@@ -117,7 +117,7 @@ def test_mesh_files_through_the_loaders_against_the_reference_kernel(tmp_path, s
     want = _ref_window(oracle_lib, sc, sky, rds, (0, 0, sc.width, sc.height))
     assert_bit_equal(want, got, f"{kind} file -> loader -> upload -> render vs render.cl")
     ids, _ = tr.debug_primary(sc.render_data(0, num_samples=1))
-    assert (ids == 1).sum() > 500  # the loaded mesh is in view
+    assert (ids == 1).sum() > 200  # the loaded mesh is in view
 
 
 def test_work_item_cap_and_64_bit_cursor(sky):
