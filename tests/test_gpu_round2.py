@@ -139,12 +139,16 @@ def test_work_item_cap_and_64_bit_cursor(sky):
     tr.clear_canvas()
     tr.accumulate(rd)
     a = tr.read_canvas()
-    assert np.isfinite(a[..., :3]).all() and a[..., :3].mean() > 0
+    # log(0) is legal in the reference arithmetic (probability 2^-32 per draw, render.cl:152): at 4.3e9 samples x ~20
+    # draws a handful of samples are inf / NaN and poison their pixel's mean -- on both sides of the parity contract
+    fin = np.isfinite(a[..., :3]).all(axis=-1)
+    assert (~fin).sum() <= 200 and a[fin][:, :3].mean() > 0
     # the mean over that many samples is the converged 2-bounce image: a 4096-sample launch agrees to Monte-Carlo noise
     tr.clear_canvas()
     tr.accumulate(sc.render_data(1, num_samples=4096, num_bounces=2))
     b = tr.read_canvas()
-    assert np.abs(a[..., :3] - b[..., :3]).mean() < 0.15 * b[..., :3].mean()
+    fin &= np.isfinite(b[..., :3]).all(axis=-1)
+    assert np.abs(a[fin][:, :3] - b[fin][:, :3]).mean() < 0.15 * b[fin][:, :3].mean()
     cnt = tr.accumulate_counted(sc.render_data(0, num_samples=1 << 12, num_bounces=1))
     assert int(cnt[0]["samples"]) == 64 * 64 * (1 << 12)
 
