@@ -62,7 +62,7 @@ static int filter_rejects(v3 v0, v3 e1, v3 e2, v3 o, v3 d, float margin_scale) {
 	float det = om_fma(d.z, np.z, om_fma(d.y, np.y, d.x * np.x));
 	float t = om_fma(d.z, m.z, om_fma(d.y, m.y, d.x * m.x));
 	float su = om_fma(e2.z, c.z, om_fma(e2.y, c.y, om_fma(e2.x, c.x, -t)));
-	float diff = su - det * 0.500001f;
+	float diff = om_fma(-det, 0.500001f, su);  /* one rounding (FFMA), as in tri_filter_sweep */
 	float w = om_fma(__builtin_fabsf(det), 0.500001f, M);
 	return (__builtin_fabsf(diff) > w) ? 1 : 0;
 }

@@ -165,25 +165,32 @@ struct TriFlt {
 #ifndef SRT_MARGIN_SCALE  // developer mutation test only: 0 removes the error margins of the sweep filter
 #define SRT_MARGIN_SCALE 1.0f
 #endif
-#ifndef SRT_RAYS_PER_ITER
-#define SRT_RAYS_PER_ITER 2
-#endif
 // The margin is formed once per triangle and tile from the LARGEST R among the parked rays (M = g * Rmax + 2e-6):
 // a larger margin only lets more triangles through.
 // m: the margin M of this triangle for the phase (g * Rmax + 2e-6, formed once per tile); cz = r2.x
+#ifndef SRT_PACKED_SLOTS  // how many of a lane's TRIS_PER_LANE triangle slots evaluate {det, t} as a packed FP32x2 chain
+#define SRT_PACKED_SLOTS 4
+#endif
+// packed: a compile-time constant at every call site (the slot loop is unrolled)
 __device__ __forceinline__ bool tri_filter_sweep(const TriFlt &r, const float m, const float4 r0, const float4 r1,
-                                                 const float cz) {
+                                                 const float cz, const bool packed) {
 	// {det, t} = d.x {n'.x, m.x} + d.y {n'.y, m.y} + d.z {n'.z, m.z}
-	const float2 dt = __ffma2_rn(make_float2(r1.x, r1.y), r.c,
-	                             __ffma2_rn(make_float2(r0.z, r0.w), r.b, __fmul2_rn(make_float2(r0.x, r0.y), r.a)));
-	const float det = dt.x;
-	const float su = fma_(r.f.x, cz, fma_(r.e.y, r1.w, fma_(r.e.x, r1.z, -dt.y)));
+	float det, t;
+	if (packed) {
+		const float2 dt = __ffma2_rn(make_float2(r1.x, r1.y), r.c,
+		                             __ffma2_rn(make_float2(r0.z, r0.w), r.b, __fmul2_rn(make_float2(r0.x, r0.y), r.a)));
+		det = dt.x, t = dt.y;
+	} else {  // the same operations, one half at a time: bit-identical
+		det = fma_(r1.x, r.c.x, fma_(r0.z, r.b.x, r0.x * r.a.x));
+		t = fma_(r1.x, r.c.y, fma_(r0.z, r.b.y, r0.x * r.a.y));
+	}
+	const float su = fma_(r.f.x, cz, fma_(r.e.y, r1.w, fma_(r.e.x, r1.z, -t)));
 	// x = su sign(det) in [-M, |det| (1 + 2e-6) + M]  <=>  |su - det k| <= |det| k + M  with k = (1 + 2e-6) / 2: the
 	// interval test as a distance from its centre.  Same decision up to a few u |det| of rounding in the centre and
-	// half-width, which the slack in k and M absorbs.  Three of these four instructions run on the FMA
-	// pipe and one on the half-rate ALU pipe, against one and three for a sign flip and two compares.  A NaN fails
-	// `>` and survives.
-	const float diff = su - det * 0.500001f;
+	// half-width, which the slack in k and M absorbs; centre and half-width are one FFMA each (the filter
+	// is not render.cl arithmetic, so nothing forbids fusing: one rounding instead of two only tightens the bound).
+	// A NaN fails `>` and survives.
+	const float diff = fma_(-det, 0.500001f, su);
 	const float w = fma_(fabsf(det), 0.500001f, m);
 	return !(fabsf(diff) > w);
 }
@@ -528,7 +535,7 @@ constexpr int RENDER_THREADS = SRT_RENDER_THREADS;
 #define SRT_TRIS_PER_LANE 4
 #endif
 #ifndef SRT_TILE_STAGES
-#define SRT_TILE_STAGES 2
+#define SRT_TILE_STAGES 1
 #endif
 constexpr int TRIS_PER_LANE = SRT_TRIS_PER_LANE;
 constexpr int TILE_TRIS = 32 * TRIS_PER_LANE;
@@ -603,14 +610,21 @@ __device__ __forceinline__ void triangle_phase(const DevScene &sc, int n, int tr
 	};
 	if (lane == 0)
 		for (int t = 0; t < min(ntiles, TILE_STAGES); ++t) issue(t);
-	if (active) {  // per-ray operands: d, R = |o|_1 + K, c = o x d for the filter; o for the exact test
-		const vec3 c = cross(o, d);
-		rays[3 * lane] = make_float4(d.x, d.x, d.y, d.y);
-		rays[3 * lane + 1] = make_float4(d.z, d.z, c.x, c.y);
-		rays[3 * lane + 2] = make_float4(c.z, o.x, o.y, o.z);
-		best[lane] = (unsigned long long)__float_as_uint(hit.t) << 32;
-	}
+	// the parked rays take DENSE slots 0 .. nrays-1 (slot = rank of the lane among the parked ones)
 	const unsigned ray_mask = __ballot_sync(FULL, active);
+	const int nrays = __popc(ray_mask);
+	const int slot = __popc(ray_mask & ((1u << lane) - 1u));
+	const uint32_t ray_bits = nrays >= 32 ? 0xffffffffu : (1u << nrays) - 1u;
+	if (active) {  // per-ray operands: d (twice, for the packed chain), c = o x d for the filter; o for the exact test
+		const vec3 c = cross(o, d);
+		rays[3 * slot] = make_float4(d.x, d.x, d.y, d.y);
+		rays[3 * slot + 1] = make_float4(d.z, d.z, c.x, c.y);
+		rays[3 * slot + 2] = make_float4(c.z, o.x, o.y, o.z);
+		best[slot] = (unsigned long long)__float_as_uint(hit.t) << 32;
+	}
+	if ((nrays & 1) && lane == 0) {  // pad to an even count: a null ray (its survivor bits are masked off)
+		rays[3 * nrays] = rays[3 * nrays + 1] = rays[3 * nrays + 2] = make_float4(0.f, 0.f, 0.f, 0.f);
+	}
 	int pair_head = 0, pair_count = 0;  // warp-uniform
 	// R = |o|_1 + K of my ray; its maximum over the parked rays (NaN -- a ray the filter cannot decide -- must win)
 	float rmax = active ? fabsf(o.x) + fabsf(o.y) + fabsf(o.z) + __ldg(&sc.model_k[shape]) : 0.0f;
@@ -642,76 +656,57 @@ __device__ __forceinline__ void triangle_phase(const DevScene &sc, int n, int tr
 				tf[q].a = r[0], tf[q].b = r[1], tf[q].c = r[2], tf[q].e = r[3], tf[q].f = r[4];
 				tf[q].f.y = fma_(tf[q].f.y, rmax, 2e-6f * SRT_MARGIN_SCALE);  // g -> M
 			}
-#if SRT_RAYS_PER_ITER == 2
-			// two parked rays per trip: half the loop overhead per ray and eight independent dependency chains
-			unsigned rm = ray_mask;
-			for (; rm & (rm - 1); rm &= rm - 1, rm &= rm - 1) {  // warp-uniform; at least two rays left
-				const int r0 = __ffs(rm) - 1, r1 = __ffs(rm & (rm - 1)) - 1;
-				const float4 a0 = rays[3 * r0], a1 = rays[3 * r0 + 1], b0 = rays[3 * r1], b1 = rays[3 * r1 + 1];
-				const float acz = reinterpret_cast<const float *>(rays + 3 * r0 + 2)[0];
-				const float bcz = reinterpret_cast<const float *>(rays + 3 * r1 + 2)[0];
-#pragma unroll
-				for (int q = 0; q < TRIS_PER_LANE; ++q) {
-					const unsigned v0 = __ballot_sync(FULL, tri_filter_sweep(tf[q], tf[q].f.y, a0, a1, acz));
-					const unsigned v1 = __ballot_sync(FULL, tri_filter_sweep(tf[q], tf[q].f.y, b0, b1, bcz));
-					if (lane == r0) cand[q] = v0;
-					if (lane == r1) cand[q] = v1;
-				}
-			}
-			if (rm) {  // odd one out
-				const int r = __ffs(rm) - 1;
-				const float4 a0 = rays[3 * r], a1 = rays[3 * r + 1];
-				const float acz = reinterpret_cast<const float *>(rays + 3 * r + 2)[0];
-#pragma unroll
-				for (int q = 0; q < TRIS_PER_LANE; ++q) {
-					const unsigned v = __ballot_sync(FULL, tri_filter_sweep(tf[q], tf[q].f.y, a0, a1, acz));
-					if (lane == r) cand[q] = v;
-				}
-			}
-#else
-			for (unsigned rm = ray_mask; rm; rm &= rm - 1) {  // warp-uniform loop over the parked rays
-				const int r = __ffs(rm) - 1;
-				const float4 a0 = rays[3 * r], a1 = rays[3 * r + 1];  // broadcast
-				const float acz = reinterpret_cast<const float *>(rays + 3 * r + 2)[0];
-#pragma unroll
-				for (int q = 0; q < TRIS_PER_LANE; ++q) {
-					const unsigned v = __ballot_sync(FULL, tri_filter_sweep(tf[q], tf[q].f.y, a0, a1, acz));
-					if (lane == r) cand[q] = v;
-				}
-			}
-#endif
-			__syncwarp();  // every lane is done reading this stage before it is refilled
+			// the tile now lives in registers: its stage is refilled BEFORE the sweep, which gives the copy a whole
+			// sweep to land (and makes a one-stage ring sufficient)
+			__syncwarp();  // every lane has read this stage
 			if (lane == 0 && t + TILE_STAGES < ntiles) issue(t + TILE_STAGES);
-			// beyond the end of the list the tile holds stale shared memory: those votes are masked
+			// two parked rays per trip (the slots are dense: an odd count is padded with a null ray whose bit is masked
+			// off below).  A lane keeps, per triangle slot, the bit mask of the RAYS its triangle survived: one predicated
+			// OR per pair -- no vote, no hand-off to an owner lane.
+			{
+				const float4 *rp = rays;
+				uint32_t bit = 1u;
+				for (int i = 0; i < nrays; i += 2, rp += 6, bit <<= 2) {  // warp-uniform
+					const float4 a0 = rp[0], a1 = rp[1], b0 = rp[3], b1 = rp[4];
+					const float acz = reinterpret_cast<const float *>(rp + 2)[0];
+					const float bcz = reinterpret_cast<const float *>(rp + 5)[0];
+#pragma unroll
+					for (int q = 0; q < TRIS_PER_LANE; ++q) {
+						if (tri_filter_sweep(tf[q], tf[q].f.y, a0, a1, acz, q < SRT_PACKED_SLOTS)) cand[q] |= bit;
+						if (tri_filter_sweep(tf[q], tf[q].f.y, b0, b1, bcz, q < SRT_PACKED_SLOTS)) cand[q] |= bit << 1;
+					}
+				}
+			}
+			// the padding ray's bit, and triangles beyond the end of the list (the tile holds stale shared memory there)
 			const int cnt = n - t * TILE_TRIS;
 #pragma unroll
-			for (int q = 0; q < TRIS_PER_LANE; ++q) {
-				const int left = cnt - q * 32;
-				cand[q] &= left >= 32 ? 0xffffffffu : (left <= 0 ? 0u : (1u << left) - 1u);
-			}
+			for (int q = 0; q < TRIS_PER_LANE; ++q) cand[q] = q * 32 + lane < cnt ? cand[q] & ray_bits : 0u;
 		}
 		// survivors -> pair ring -> exact tests, 32 at a time; after the last tile (t == ntiles) the ring is emptied
 		for (;;) {
 			int mine = 0;
 #pragma unroll
 			for (int q = 0; q < TRIS_PER_LANE; ++q) mine += __popc(cand[q]);
-			int incl = mine;  // inclusive prefix sum over the lanes
-#pragma unroll
-			for (int off = 1; off < 32; off <<= 1) {
-				const int up = __shfl_up_sync(FULL, incl, off);
-				if (lane >= off) incl += up;
-			}
-			const int total = __shfl_sync(FULL, incl, 31);
+			int total = 0;
 			const int room = PAIR_SLOTS - pair_count;
-			if (total) {
+			if (__any_sync(FULL, mine != 0)) {  // (a tile without survivors skips the scan altogether)
+				int incl = mine;  // inclusive prefix sum over the lanes
+#pragma unroll
+				for (int off = 1; off < 32; off <<= 1) {
+					const int up = __shfl_up_sync(FULL, incl, off);
+					if (lane >= off) incl += up;
+				}
+				total = __shfl_sync(FULL, incl, 31);
 				int rank = incl - mine;  // my first survivor's rank among the warp's
 #pragma unroll
 				for (int q = 0; q < TRIS_PER_LANE; ++q) {
-					uint32_t c = cand[q];
-					const uint32_t base = ((uint32_t)lane << 27) | (uint32_t)(t * TILE_TRIS + q * 32);
+					uint32_t c = cand[q];  // bit r: my triangle of slot q survived the filter for the ray in slot r
+					const uint32_t base = (uint32_t)(t * TILE_TRIS + q * 32 + lane);
+					// (one loop over all four masks of a lane was tried: fewer trips, but the slot bookkeeping made each
+					// trip dearer -- 9 % slower on the ~1k-triangle meshes; so was an L1 prefetch of the survivors' operands)
 					while (c && rank < room) {
-						SRT_ASSERT(rank >= 0 && pair_count + rank < PAIR_SLOTS && t * TILE_TRIS + q * 32 + (__ffs(c) - 1) < n);
-						pairs[(pair_head + pair_count + rank) & (PAIR_SLOTS - 1)] = base + (__ffs(c) - 1);
+						SRT_ASSERT(rank >= 0 && pair_count + rank < PAIR_SLOTS && (int)base < n && __ffs(c) - 1 < nrays);
+						pairs[(pair_head + pair_count + rank) & (PAIR_SLOTS - 1)] = base | ((uint32_t)(__ffs(c) - 1) << 27);
 						c &= c - 1;
 						++rank;
 					}
@@ -726,7 +721,7 @@ __device__ __forceinline__ void triangle_phase(const DevScene &sc, int n, int tr
 				if (lane < m) {
 					const uint32_t pr = pairs[(pair_head + lane) & (PAIR_SLOTS - 1)];
 					const int r = pr >> 27, j = pr & (MAX_SWEEP_TRIS - 1);
-					SRT_ASSERT(j >= 0 && j < n && ((ray_mask >> r) & 1u));
+					SRT_ASSERT(j >= 0 && j < n && r < nrays);
 					const float4 q0 = rays[3 * r], q1 = rays[3 * r + 1], q2 = rays[3 * r + 2];
 					exact_pair(__ldg(exact + 3 * (size_t)j), __ldg(exact + 3 * (size_t)j + 1), __ldg(exact + 3 * (size_t)j + 2),
 					           make_float4(q2.y, q2.z, q2.w, 0.f), make_float4(q0.x, q0.z, q1.x, 0.f), best + r, j);
@@ -740,7 +735,7 @@ __device__ __forceinline__ void triangle_phase(const DevScene &sc, int n, int tr
 	}
 	SRT_ASSERT(pair_count == 0);
 	if (active) {
-		const unsigned long long k = best[lane];
+		const unsigned long long k = best[slot];
 		const unsigned tri1 = (unsigned)k;
 		SRT_ASSERT(tri1 <= (unsigned)n && (k >> 32) <= (unsigned long long)__float_as_uint(hit.t));
 		if (tri1) {
