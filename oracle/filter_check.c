@@ -15,6 +15,9 @@
  * few ulps .. 1e-3 of 0 or 1, or whose direction is within 1e-7 .. 1e-2 of the triangle's plane (det ~ 0), for
  * triangles of size 1e-4 .. 1e3 at distances up to 1e6 from the origin, plus uniformly random pairs.
  *
+ * filter_check_uv does the same for the two-strip filter of small models (tri_filter_sweep_uv: u AND v ranges) against
+ * the reference's u, v, u + v and t tests together, with extra pairs aimed at v ~ 0 and v ~ 1.
+ *
  *   filter_check(n_pairs, seed, margin_scale, out[4]):  out = {pairs, filter rejects, violations, reference rejects}
  *   margin_scale = 1 is the kernel's margin; 0 removes it (the test uses that to show the margins matter).
  */
@@ -67,9 +70,49 @@ static int filter_rejects(v3 v0, v3 e1, v3 e2, v3 o, v3 d, float margin_scale) {
 	return (__builtin_fabsf(diff) > w) ? 1 : 0;
 }
 
+/* reference decision through the u AND the v / u+v range tests, render.cl:250-268: 1 = the pair cannot become a hit */
+static int reference_rejects_uv(v3 v0, v3 e1, v3 e2, v3 o, v3 d) {
+	v3 h = v3_cross(d, e2);
+	float a = v3_dot(e1, h);
+	if (a == 0.0f) return 1;
+	float f = 1.0f / a;
+	v3 s = v3_sub(o, v0);
+	float u = f * v3_dot(s, h);
+	if (u < 0.0f || u > 1.0f) return 1;
+	v3 q = v3_cross(s, e1);
+	float v = f * v3_dot(d, q);
+	if (v < 0.0f || u + v > 1.0f) return 1;
+	float t = f * v3_dot(e2, q);
+	return (t > 0.0f && t < __builtin_inff()) ? 0 : 1; /* a NaN / infinite / non-positive t is no hit either (:270) */
+}
+
+/* the two-strip sweep filter for small models: record as prepare_triangles_kernel builds it (n', -m, -m1, e2, e1, one
+ * common margin scale), test as tri_filter_sweep_uv evaluates it.  With m1 = e1 x v0:  v det = d . m1 - e1 . c. */
+static int filter_rejects_uv(v3 v0, v3 e1, v3 e2, v3 o, v3 d, float margin_scale) {
+	const float U = 5.9604644775390625e-8f;
+	v3 np = v3_cross(e2, e1), m = v3_cross(e2, v0), m1 = v3_cross(e1, v0);
+	float n1e1 = __builtin_fabsf(e1.x) + __builtin_fabsf(e1.y) + __builtin_fabsf(e1.z);
+	float n1e2 = __builtin_fabsf(e2.x) + __builtin_fabsf(e2.y) + __builtin_fabsf(e2.z);
+	float n1v0 = __builtin_fabsf(v0.x) + __builtin_fabsf(v0.y) + __builtin_fabsf(v0.z);
+	float emax = n1e1 > n1e2 ? n1e1 : n1e2;
+	float g = 48.0f * margin_scale * U * emax;
+	float k = n1v0 + 3.0f * emax;
+	float r = __builtin_fabsf(o.x) + __builtin_fabsf(o.y) + __builtin_fabsf(o.z) + k;
+	float M = om_fma(g, r, 2e-6f * margin_scale);
+	v3 c = v3_cross(o, d);
+	float det = om_fma(d.z, np.z, om_fma(d.y, np.y, d.x * np.x));
+	float nt = om_fma(d.z, -m.z, om_fma(d.y, -m.y, d.x * -m.x));    /* -t  = d . (-m)  */
+	float nt1 = om_fma(d.z, -m1.z, om_fma(d.y, -m1.y, d.x * -m1.x)); /* -t1 = d . (-m1) */
+	float su = om_fma(c.z, e2.z, om_fma(c.y, e2.y, om_fma(c.x, e2.x, nt)));   /*  u det */
+	float sv = om_fma(c.z, e1.z, om_fma(c.y, e1.y, om_fma(c.x, e1.x, nt1))); /* -v det */
+	float du = om_fma(-det, 0.500001f, su), dv = om_fma(det, 0.500001f, sv);
+	float w = om_fma(__builtin_fabsf(det), 0.500001f, M);
+	return (__builtin_fabsf(du) > w || __builtin_fabsf(dv) > w) ? 1 : 0;
+}
+
 static inline v3 f3d(double x, double y, double z) { return v3_make((float)x, (float)y, (float)z); }
 
-void filter_check(uint64_t n_pairs, uint64_t seed, float margin_scale, uint64_t out[4]) {
+static void filter_check_impl(uint64_t n_pairs, uint64_t seed, float margin_scale, uint64_t out[4], int uv) {
 	uint64_t pairs = 0, rejects = 0, violations = 0, ref_rejects = 0;
 #pragma omp parallel reduction(+ : pairs, rejects, violations, ref_rejects)
 	{
@@ -95,15 +138,17 @@ void filter_check(uint64_t n_pairs, uint64_t seed, float margin_scale, uint64_t 
 			/* ray: origin at distance 0.1 .. 100 sizes, aimed at a chosen point of the triangle's plane */
 			double dist = size * logu(&s, 0.1, 100.0);
 			double ox = cx + dist * srand1(&s) + off * 0.1 * srand1(&s), oy = cy + dist * srand1(&s), oz = cz + dist * srand1(&s);
-			int mode = (int)(splitmix(&s) % 5);
+			int mode = (int)(splitmix(&s) % (uv ? 7 : 5));
 			double u, v;
 			if (mode == 0) { u = 3 * srand1(&s), v = 3 * srand1(&s); }                       /* anywhere */
 			else if (mode == 1) { u = logu(&s, 1e-9, 1e-3) * srand1(&s), v = 2 * srand1(&s); } /* u ~ 0 */
 			else if (mode == 2) { u = 1 + logu(&s, 1e-9, 1e-3) * srand1(&s), v = 2 * srand1(&s); } /* u ~ 1 */
+			else if (mode == 5) { v = logu(&s, 1e-9, 1e-3) * srand1(&s), u = 2 * srand1(&s); }     /* v ~ 0 */
+			else if (mode == 6) { v = 1 + logu(&s, 1e-9, 1e-3) * srand1(&s), u = 2 * srand1(&s); } /* v ~ 1 */
 			else { u = 1.5 * srand1(&s), v = 1.5 * srand1(&s); }
 			double px = cx + u * ax + v * bx, py = cy + u * ay + v * by, pz = cz + u * az + v * bz;
 			double dx = px - ox, dy = py - oy, dz = pz - oz;
-			if (mode >= 3) { /* grazing: direction almost in the triangle's plane */
+			if (mode == 3 || mode == 4) { /* grazing: direction almost in the triangle's plane */
 				double e = logu(&s, 1e-7, 1e-2), a = srand1(&s), b = srand1(&s);
 				double nx = ay * bz - az * by, ny = az * bx - ax * bz, nz = ax * by - ay * bx;
 				double nn = __builtin_sqrt(nx * nx + ny * ny + nz * nz) + 1e-300;
@@ -113,12 +158,20 @@ void filter_check(uint64_t n_pairs, uint64_t seed, float margin_scale, uint64_t 
 			v3 d = v3_normalize(f3d(dx, dy, dz)); /* directions reach the intersection code normalised */
 			if (!(d.x == d.x)) continue;
 			pairs++;
-			int fr = filter_rejects(v0, e1, e2, o, d, margin_scale);
-			int rr = reference_rejects_u(v0, e1, e2, o, d);
+			int fr = uv ? filter_rejects_uv(v0, e1, e2, o, d, margin_scale) : filter_rejects(v0, e1, e2, o, d, margin_scale);
+			int rr = uv ? reference_rejects_uv(v0, e1, e2, o, d) : reference_rejects_u(v0, e1, e2, o, d);
 			rejects += (uint64_t)fr;
 			ref_rejects += (uint64_t)rr;
 			if (fr && !rr) violations++;
 		}
 	}
 	out[0] = pairs, out[1] = rejects, out[2] = violations, out[3] = ref_rejects;
+}
+
+void filter_check(uint64_t n_pairs, uint64_t seed, float margin_scale, uint64_t out[4]) {
+	filter_check_impl(n_pairs, seed, margin_scale, out, 0);
+}
+/* the two-strip (u and v) filter against the reference's u, v, u+v and t tests together */
+void filter_check_uv(uint64_t n_pairs, uint64_t seed, float margin_scale, uint64_t out[4]) {
+	filter_check_impl(n_pairs, seed, margin_scale, out, 1);
 }

@@ -47,7 +47,8 @@ struct DevScene {
 	const float4 *shape_b;    // sphere {-}        | plane {n.xyz, -}  | model {bmax.xyz, -}
 	const float4 *tri_hot;    // 3 per triangle, 48 B stride: world-space v0, e1 = v1-v0, e2 = v2-v0 (+1 pad triangle)
 	const float2 *tri_flt;    // 5 per triangle, 40 B stride: the sweep filter's record n', g, e2, m (tri_filter_sweep)
-	const float *model_k;     // per shape slot: max over the model's triangles of |v0|_1 + 3 |e1|_1 (filter margin)
+	const float4 *tri_uv;     // 5 per triangle, 80 B stride: the two-strip filter's record (tri_filter_sweep_uv)
+	const float *model_k;     // per shape slot: max over the model's triangles of |v0|_1 + 3 max(|e1|_1, |e2|_1) (filter margin)
 	const float4 *tri_n;      // 3 per triangle: object-space vertex normals (cold: winner only)
 	const float4 *model_xf;   // 4 per shape slot: model matrix columns      (cold)
 	const float4 *materials;  // 4 per material: the reference's 64-byte record as 4 x float4
@@ -193,6 +194,37 @@ __device__ __forceinline__ bool tri_filter_sweep(const TriFlt &r, const float m,
 	const float diff = fma_(-det, 0.500001f, su);
 	const float w = fma_(fabsf(det), 0.500001f, m);
 	return !(fabsf(diff) > w);
+}
+// Two-strip filter for models with few, large triangles.  The u strip alone lets through every ray that crosses the
+// infinite band between the triangle's edge e2 and its parallel through v1 -- on a ~1k-triangle mesh about 18 pairs for
+// each real hit, and pushing / exact-testing those survivors costs more than the sweep itself.  The v range is bounded
+// the same way: with m1 = e1 x v0,
+//   v det = d . ((o - v0) x e1) = d . m1 - e1 . (o x d)
+// so -v det =: sv costs six more multiply-adds, evaluated TOGETHER with su as packed FP32x2 chains:
+//   {-t, -t1} = d . {-m, -m1}      {su, sv} = c . {e2, e1} + {-t, -t1}      (c = o x d)
+// and the pair is dropped when u or v is certainly outside [0, 1] (then render.cl:261 / :266 rejects it: v > 1 with
+// u >= 0 gives u + v > 1).  The error bounds are those of the u test with e1 in the place of e2, so ONE margin
+// M = g R + 2e-6 with g = 48u max(|e1|_1, |e2|_1) and K = max(|v0|_1 + 3 max(|e1|_1, |e2|_1)) covers both
+// (oracle/filter_check.c checks this filter too: 1e8 adversarial pairs, no wrong reject).  Survivors: ~2 per real hit.
+//   record (80 B): q0 = {n'.x, n'.y, n'.z, g}  q1 = {-m.x, -m1.x, -m.y, -m1.y}  q2 = {-m.z, -m1.z, e2.x, e1.x}
+//                  q3 = {e2.y, e1.y, e2.z, e1.z}  (+16 B pad: the 80 B stride keeps the lanes' LDS.128 conflict-free)
+//   ray (64 B):    r0 = {d.x, d.x, d.y, d.y}  r1 = {d.z, d.z, c.x, c.x}  r2 = {c.y, c.y, c.z, c.z}  r3 = {o, -}
+struct TriUV {
+	float4 q0, q1, q2, q3;
+};
+__device__ __forceinline__ bool tri_filter_sweep_uv(const TriUV &r, const float m, const float4 r0, const float4 r1,
+                                                    const float4 r2) {
+	const float det = fma_(r1.x, r.q0.z, fma_(r0.z, r.q0.y, r0.x * r.q0.x));
+	const float2 nt = __ffma2_rn(make_float2(r1.x, r1.y), make_float2(r.q2.x, r.q2.y),
+	                             __ffma2_rn(make_float2(r0.z, r0.w), make_float2(r.q1.z, r.q1.w),
+	                                        __fmul2_rn(make_float2(r0.x, r0.y), make_float2(r.q1.x, r.q1.y))));
+	const float2 ss = __ffma2_rn(make_float2(r2.z, r2.w), make_float2(r.q3.z, r.q3.w),
+	                             __ffma2_rn(make_float2(r2.x, r2.y), make_float2(r.q3.x, r.q3.y),
+	                                        __ffma2_rn(make_float2(r1.z, r1.w), make_float2(r.q2.z, r.q2.w), nt)));
+	const float du = fma_(-det, 0.500001f, ss.x);  // u det - det k
+	const float dv = fma_(det, 0.500001f, ss.y);   // -(v det - det k)
+	const float w = fma_(fabsf(det), 0.500001f, m);
+	return !(fabsf(du) > w) && !(fabsf(dv) > w);  // NaNs fail `>` and survive
 }
 __device__ __forceinline__ void test_triangle(const float4 v0, const float4 e1, const float4 e2, vec3 o, vec3 d,
                                               int shape, int tri, Hit &hit) {
@@ -541,9 +573,22 @@ constexpr int TRIS_PER_LANE = SRT_TRIS_PER_LANE;
 constexpr int TILE_TRIS = 32 * TRIS_PER_LANE;
 constexpr int TILE_STAGES = SRT_TILE_STAGES;
 constexpr int FLT_BYTES = 40;                 // filter record of one triangle (TriFlt)
-constexpr int TILE_BYTES = TILE_TRIS * FLT_BYTES;
+// Two-strip (u AND v) variant of the filter for models of at most UV_MAX_TRIS triangles (tri_filter_sweep_uv):
+// 80-byte records (TriUV), fewer triangles per lane because a record is 16 registers instead of 10.
+#ifndef SRT_TRIS_PER_LANE_UV
+#define SRT_TRIS_PER_LANE_UV 4
+#endif
+#ifndef SRT_UV_MAX_TRIS
+#define SRT_UV_MAX_TRIS 20000
+#endif
+constexpr int TRIS_PER_LANE_UV = SRT_TRIS_PER_LANE_UV;
+constexpr int TILE_TRIS_UV = 32 * TRIS_PER_LANE_UV;
+constexpr int UV_BYTES = 80;
+constexpr int UV_MAX_TRIS = SRT_UV_MAX_TRIS;
+static_assert(TRIS_PER_LANE_UV <= TRIS_PER_LANE, "the survivor masks are sized for TRIS_PER_LANE slots");
+constexpr int TILE_BYTES = TILE_TRIS * FLT_BYTES > TILE_TRIS_UV * UV_BYTES ? TILE_TRIS * FLT_BYTES : TILE_TRIS_UV * UV_BYTES;
 constexpr int RING_BYTES = TILE_STAGES * TILE_BYTES;
-constexpr int RAYS_BYTES = 32 * 48;           // 32 rays x {d, R} {o x d, -} {o, -}
+constexpr int RAYS_BYTES = 32 * 64;           // 32 rays x 4 float4: the filter's operands (3) and the origin for the exact test
 constexpr int PAIR_SLOTS = 256;               // ring of filter survivors (ray << 27 | triangle) awaiting the exact test
 constexpr int PAIRS_BYTES = PAIR_SLOTS * 4;
 constexpr int BEST_BYTES = 32 * 8;            // per parked ray: (t bits << 32 | triangle + 1), minimised atomically
@@ -591,7 +636,13 @@ __device__ __forceinline__ void exact_pair(const float4 v0, const float4 e1, con
 }
 
 // n, tri_begin, shape: the model being swept (warp-uniform); active: this lane's ray is parked at it.
-__device__ __forceinline__ void triangle_phase(const DevScene &sc, int n, int tri_begin, int shape, bool active, vec3 o,
+// UV: which filter the model is swept with (and with it the record size and the tile geometry); two instantiations,
+// of which a scene normally exercises one, so the hot instruction footprint stays that of a single phase.
+#ifndef SRT_PHASE_ATTR
+#define SRT_PHASE_ATTR __forceinline__
+#endif
+template <bool UV>
+__device__ SRT_PHASE_ATTR void triangle_phase(const DevScene &sc, int n, int tri_begin, int shape, bool active, vec3 o,
                                                vec3 d, Hit &hit, unsigned char *wsmem, uint32_t wsmem_s, uint32_t bars_s,
                                                uint32_t &parity, int lane) {
 	const unsigned FULL = 0xffffffffu;
@@ -599,14 +650,20 @@ __device__ __forceinline__ void triangle_phase(const DevScene &sc, int n, int tr
 	float4 *rays = reinterpret_cast<float4 *>(wsmem + RING_BYTES);
 	uint32_t *pairs = reinterpret_cast<uint32_t *>(wsmem + RING_BYTES + RAYS_BYTES);
 	unsigned long long *best = reinterpret_cast<unsigned long long *>(wsmem + RING_BYTES + RAYS_BYTES + PAIRS_BYTES);
-	const char *src = reinterpret_cast<const char *>(sc.tri_flt + 5 * (size_t)tri_begin);  // tri_begin is even: 16 B aligned
+	constexpr bool uv = UV;
+	constexpr int tile_tris = uv ? TILE_TRIS_UV : TILE_TRIS;
+	constexpr int rec_bytes = uv ? UV_BYTES : FLT_BYTES;
+	constexpr int tile_bytes = tile_tris * rec_bytes;
+	// tri_begin is even: both record arrays start 16-byte aligned
+	const char *src = uv ? reinterpret_cast<const char *>(sc.tri_uv + 5 * (size_t)tri_begin)
+	                     : reinterpret_cast<const char *>(sc.tri_flt + 5 * (size_t)tri_begin);
 	const float4 *exact = sc.tri_hot + 3 * (size_t)tri_begin;  // survivors fetch the reference operands from L1/L2
-	const int ntiles = (n + TILE_TRIS - 1) / TILE_TRIS;
+	const int ntiles = (n + tile_tris - 1) / tile_tris;
 	auto issue = [&](int t) {
 		const int st = t % TILE_STAGES;
-		const uint32_t bytes = ((uint32_t)min(TILE_TRIS, n - t * TILE_TRIS) * FLT_BYTES + 15u) & ~15u;  // the array is padded
-		SRT_ASSERT(bytes > 0 && bytes <= (uint32_t)TILE_BYTES && ((size_t)(src + (size_t)t * TILE_BYTES) & 15) == 0);
-		bulk_load_tile(wsmem_s + st * TILE_BYTES, src + (size_t)t * TILE_BYTES, bytes, bars_s + st * 8);
+		const uint32_t bytes = ((uint32_t)min(tile_tris, n - t * tile_tris) * rec_bytes + 15u) & ~15u;  // the arrays are padded
+		SRT_ASSERT(bytes > 0 && bytes <= (uint32_t)TILE_BYTES && ((size_t)(src + (size_t)t * tile_bytes) & 15) == 0);
+		bulk_load_tile(wsmem_s + st * TILE_BYTES, src + (size_t)t * tile_bytes, bytes, bars_s + st * 8);
 	};
 	if (lane == 0)
 		for (int t = 0; t < min(ntiles, TILE_STAGES); ++t) issue(t);
@@ -615,15 +672,16 @@ __device__ __forceinline__ void triangle_phase(const DevScene &sc, int n, int tr
 	const int nrays = __popc(ray_mask);
 	const int slot = __popc(ray_mask & ((1u << lane) - 1u));
 	const uint32_t ray_bits = nrays >= 32 ? 0xffffffffu : (1u << nrays) - 1u;
-	if (active) {  // per-ray operands: d (twice, for the packed chain), c = o x d for the filter; o for the exact test
+	if (active) {  // per-ray operands (64 B): d twice for the packed chains, c = o x d; the origin for the exact test
 		const vec3 c = cross(o, d);
-		rays[3 * slot] = make_float4(d.x, d.x, d.y, d.y);
-		rays[3 * slot + 1] = make_float4(d.z, d.z, c.x, c.y);
-		rays[3 * slot + 2] = make_float4(c.z, o.x, o.y, o.z);
+		rays[4 * slot] = make_float4(d.x, d.x, d.y, d.y);
+		rays[4 * slot + 1] = uv ? make_float4(d.z, d.z, c.x, c.x) : make_float4(d.z, d.z, c.x, c.y);
+		rays[4 * slot + 2] = uv ? make_float4(c.y, c.y, c.z, c.z) : make_float4(c.z, 0.f, 0.f, 0.f);
+		rays[4 * slot + 3] = make_float4(o.x, o.y, o.z, 0.f);
 		best[slot] = (unsigned long long)__float_as_uint(hit.t) << 32;
 	}
 	if ((nrays & 1) && lane == 0) {  // pad to an even count: a null ray (its survivor bits are masked off)
-		rays[3 * nrays] = rays[3 * nrays + 1] = rays[3 * nrays + 2] = make_float4(0.f, 0.f, 0.f, 0.f);
+		rays[4 * nrays] = rays[4 * nrays + 1] = rays[4 * nrays + 2] = rays[4 * nrays + 3] = make_float4(0.f, 0.f, 0.f, 0.f);
 	}
 	int pair_head = 0, pair_count = 0;  // warp-uniform
 	// R = |o|_1 + K of my ray; its maximum over the parked rays (NaN -- a ray the filter cannot decide -- must win)
@@ -647,38 +705,59 @@ __device__ __forceinline__ void triangle_phase(const DevScene &sc, int n, int tr
 			const int st = t % TILE_STAGES;
 			mbar_wait(bars_s + st * 8, (parity >> st) & 1u);
 			parity ^= 1u << st;
-			const float2 *tile = reinterpret_cast<const float2 *>(tiles + st * TILE_BYTES);
-			// my triangles of this tile: slot q holds triangle q*32 + lane (bit `lane` of the slot's vote)
-			TriFlt tf[TRIS_PER_LANE];
+			const unsigned char *tile = tiles + st * TILE_BYTES;
+			if (!uv) {
+				// my triangles of this tile: slot q holds triangle q*32 + lane
+				TriFlt tf[TRIS_PER_LANE];
 #pragma unroll
-			for (int q = 0; q < TRIS_PER_LANE; ++q) {
-				const float2 *r = tile + 5 * (q * 32 + lane);  // 40 B stride: conflict-free LDS.64
-				tf[q].a = r[0], tf[q].b = r[1], tf[q].c = r[2], tf[q].e = r[3], tf[q].f = r[4];
-				tf[q].f.y = fma_(tf[q].f.y, rmax, 2e-6f * SRT_MARGIN_SCALE);  // g -> M
-			}
-			// the tile now lives in registers: its stage is refilled BEFORE the sweep, which gives the copy a whole
-			// sweep to land (and makes a one-stage ring sufficient)
-			__syncwarp();  // every lane has read this stage
-			if (lane == 0 && t + TILE_STAGES < ntiles) issue(t + TILE_STAGES);
-			// two parked rays per trip (the slots are dense: an odd count is padded with a null ray whose bit is masked
-			// off below).  A lane keeps, per triangle slot, the bit mask of the RAYS its triangle survived: one predicated
-			// OR per pair -- no vote, no hand-off to an owner lane.
-			{
+				for (int q = 0; q < TRIS_PER_LANE; ++q) {
+					const float2 *r = reinterpret_cast<const float2 *>(tile) + 5 * (q * 32 + lane);  // 40 B stride: conflict-free LDS.64
+					tf[q].a = r[0], tf[q].b = r[1], tf[q].c = r[2], tf[q].e = r[3], tf[q].f = r[4];
+					tf[q].f.y = fma_(tf[q].f.y, rmax, 2e-6f * SRT_MARGIN_SCALE);  // g -> M
+				}
+				// the tile now lives in registers: its stage is refilled BEFORE the sweep, which gives the copy a whole
+				// sweep to land (and makes a one-stage ring sufficient)
+				__syncwarp();  // every lane has read this stage
+				if (lane == 0 && t + TILE_STAGES < ntiles) issue(t + TILE_STAGES);
+				// two parked rays per trip (the slots are dense: an odd count is padded with a null ray whose bit is masked
+				// off below).  A lane keeps, per triangle slot, the bit mask of the RAYS its triangle survived: one
+				// predicated OR per pair -- no vote, no hand-off to an owner lane.
 				const float4 *rp = rays;
 				uint32_t bit = 1u;
-				for (int i = 0; i < nrays; i += 2, rp += 6, bit <<= 2) {  // warp-uniform
-					const float4 a0 = rp[0], a1 = rp[1], b0 = rp[3], b1 = rp[4];
+				for (int i = 0; i < nrays; i += 2, rp += 8, bit <<= 2) {  // warp-uniform
+					const float4 a0 = rp[0], a1 = rp[1], b0 = rp[4], b1 = rp[5];
 					const float acz = reinterpret_cast<const float *>(rp + 2)[0];
-					const float bcz = reinterpret_cast<const float *>(rp + 5)[0];
+					const float bcz = reinterpret_cast<const float *>(rp + 6)[0];
 #pragma unroll
 					for (int q = 0; q < TRIS_PER_LANE; ++q) {
 						if (tri_filter_sweep(tf[q], tf[q].f.y, a0, a1, acz, q < SRT_PACKED_SLOTS)) cand[q] |= bit;
 						if (tri_filter_sweep(tf[q], tf[q].f.y, b0, b1, bcz, q < SRT_PACKED_SLOTS)) cand[q] |= bit << 1;
 					}
 				}
+			} else {
+				// the same sweep with the two-strip filter: 80-byte records, TRIS_PER_LANE_UV triangles per lane
+				TriUV tv[TRIS_PER_LANE_UV];
+#pragma unroll
+				for (int q = 0; q < TRIS_PER_LANE_UV; ++q) {
+					const float4 *r = reinterpret_cast<const float4 *>(tile) + 5 * (q * 32 + lane);  // 80 B stride: conflict-free LDS.128
+					tv[q].q0 = r[0], tv[q].q1 = r[1], tv[q].q2 = r[2], tv[q].q3 = r[3];
+					tv[q].q0.w = fma_(tv[q].q0.w, rmax, 2e-6f * SRT_MARGIN_SCALE);  // g -> M
+				}
+				__syncwarp();
+				if (lane == 0 && t + TILE_STAGES < ntiles) issue(t + TILE_STAGES);
+				const float4 *rp = rays;
+				uint32_t bit = 1u;
+				for (int i = 0; i < nrays; i += 2, rp += 8, bit <<= 2) {  // warp-uniform
+					const float4 a0 = rp[0], a1 = rp[1], a2 = rp[2], b0 = rp[4], b1 = rp[5], b2 = rp[6];
+#pragma unroll
+					for (int q = 0; q < TRIS_PER_LANE_UV; ++q) {
+						if (tri_filter_sweep_uv(tv[q], tv[q].q0.w, a0, a1, a2)) cand[q] |= bit;
+						if (tri_filter_sweep_uv(tv[q], tv[q].q0.w, b0, b1, b2)) cand[q] |= bit << 1;
+					}
+				}
 			}
 			// the padding ray's bit, and triangles beyond the end of the list (the tile holds stale shared memory there)
-			const int cnt = n - t * TILE_TRIS;
+			const int cnt = min(n - t * tile_tris, tile_tris);
 #pragma unroll
 			for (int q = 0; q < TRIS_PER_LANE; ++q) cand[q] = q * 32 + lane < cnt ? cand[q] & ray_bits : 0u;
 		}
@@ -701,7 +780,7 @@ __device__ __forceinline__ void triangle_phase(const DevScene &sc, int n, int tr
 #pragma unroll
 				for (int q = 0; q < TRIS_PER_LANE; ++q) {
 					uint32_t c = cand[q];  // bit r: my triangle of slot q survived the filter for the ray in slot r
-					const uint32_t base = (uint32_t)(t * TILE_TRIS + q * 32 + lane);
+					const uint32_t base = (uint32_t)(t * tile_tris + q * 32 + lane);
 					// (one loop over all four masks of a lane was tried: fewer trips, but the slot bookkeeping made each
 					// trip dearer -- 9 % slower on the ~1k-triangle meshes; so was an L1 prefetch of the survivors' operands)
 					while (c && rank < room) {
@@ -722,9 +801,9 @@ __device__ __forceinline__ void triangle_phase(const DevScene &sc, int n, int tr
 					const uint32_t pr = pairs[(pair_head + lane) & (PAIR_SLOTS - 1)];
 					const int r = pr >> 27, j = pr & (MAX_SWEEP_TRIS - 1);
 					SRT_ASSERT(j >= 0 && j < n && r < nrays);
-					const float4 q0 = rays[3 * r], q1 = rays[3 * r + 1], q2 = rays[3 * r + 2];
-					exact_pair(__ldg(exact + 3 * (size_t)j), __ldg(exact + 3 * (size_t)j + 1), __ldg(exact + 3 * (size_t)j + 2),
-					           make_float4(q2.y, q2.z, q2.w, 0.f), make_float4(q0.x, q0.z, q1.x, 0.f), best + r, j);
+					const float4 q0 = rays[4 * r], q1 = rays[4 * r + 1], q3 = rays[4 * r + 3];
+					exact_pair(__ldg(exact + 3 * (size_t)j), __ldg(exact + 3 * (size_t)j + 1), __ldg(exact + 3 * (size_t)j + 2), q3,
+					           make_float4(q0.x, q0.z, q1.x, 0.f), best + r, j);
 				}
 				pair_head = (pair_head + m) & (PAIR_SLOTS - 1);
 				pair_count -= m;
@@ -1017,7 +1096,10 @@ render_kernel(const __grid_constant__ RenderParams p, const __grid_constant__ De
 				const int model = 0xfffff - (best & 0xfffff);
 				const int4 hdr = __ldg(&sc.shape_hdr[model]);
 				const bool active = park == model;
-				triangle_phase(sc, hdr.w, hdr.z, model, active, o, d, hit, wsmem, wsmem_s, bars_s, parity, lane);
+				if (hdr.w <= UV_MAX_TRIS)  // few, large triangles: the two-strip filter pays for itself (warp-uniform)
+					triangle_phase<true>(sc, hdr.w, hdr.z, model, active, o, d, hit, wsmem, wsmem_s, bars_s, parity, lane);
+				else
+					triangle_phase<false>(sc, hdr.w, hdr.z, model, active, o, d, hit, wsmem, wsmem_s, bars_s, parity, lane);
 				if (active) {
 					scan_at = park + 1;
 					park = -1;
@@ -1122,7 +1204,8 @@ struct ModelSpan {
 __global__ void __launch_bounds__(256)
 prepare_triangles_kernel(const float4 *__restrict__ aos /* 6 float4 per triangle */, const ModelSpan *__restrict__ spans,
                          int n_spans, int total, const float4 *__restrict__ model_xf, float4 *__restrict__ hot_out,
-                         float2 *__restrict__ flt_out, float *__restrict__ model_k, float4 *__restrict__ n_out) {
+                         float2 *__restrict__ flt_out, float4 *__restrict__ uv_out, float *__restrict__ model_k,
+                         float4 *__restrict__ n_out) {
 	int g = blockIdx.x * blockDim.x + threadIdx.x;
 	if (g >= total) return;
 	int lo = 0, hi = n_spans - 1;  // last span with dst_begin <= g
@@ -1159,7 +1242,16 @@ prepare_triangles_kernel(const float4 *__restrict__ aos /* 6 float4 per triangle
 	r[2] = make_float2(np.z, m.z);
 	r[3] = make_float2(e2.x, e2.y);
 	r[4] = make_float2(e2.z, 48.0f * SRT_MARGIN_SCALE * U * n1e2);
-	const float k = n1v0 + 3.0f * n1e1;  // non-negative (or NaN, which the filter then passes): orders like its bits
+	// record of the two-strip filter (tri_filter_sweep_uv): n', -m, -m1 = -(e1 x v0), e2, e1, one margin scale for both strips
+	const vec3 mv = cross(e1, w[0]);
+	const float emax = n1e1 > n1e2 || n1e1 != n1e1 ? n1e1 : n1e2;  // a NaN wins: the filter then passes everything
+	float4 *q = uv_out + 5 * (size_t)g;
+	q[0] = make_float4(np.x, np.y, np.z, 48.0f * SRT_MARGIN_SCALE * U * emax);
+	q[1] = make_float4(-m.x, -mv.x, -m.y, -mv.y);
+	q[2] = make_float4(-m.z, -mv.z, e2.x, e1.x);
+	q[3] = make_float4(e2.y, e1.y, e2.z, e1.z);
+	q[4] = make_float4(0.f, 0.f, 0.f, 0.f);
+	const float k = n1v0 + 3.0f * emax;  // non-negative (or NaN, which the filter then passes): orders like its bits
 	atomicMax(reinterpret_cast<unsigned int *>(model_k + sp.shape), __float_as_uint(k == k ? k : __int_as_float(0x7f800000)));
 }
 

@@ -79,6 +79,7 @@ struct srt_tracer {
 	DevBuf<float4> shape_a, shape_b, model_xf, materials;
 	DevBuf<float4> tri_aos, tri_hot, tri_n;
 	DevBuf<float2> tri_flt;  // 5 per SoA triangle (40 B filter records) + 16 B of padding
+	DevBuf<float4> tri_uv;   // 5 per SoA triangle (80 B two-strip filter records)
 	DevBuf<float> model_k;   // per shape slot
 	DevBuf<float4> scratch;  // one float4 per (pixel, sample) of a launch
 	DevBuf<srt::ModelSpan> spans;
@@ -137,6 +138,7 @@ srt::DevScene dev_scene(const srt_tracer *t) {
 	s.shape_b = t->shape_b.ptr;
 	s.tri_hot = t->tri_hot.ptr;
 	s.tri_flt = t->tri_flt.ptr;
+	s.tri_uv = t->tri_uv.ptr;
 	s.model_k = t->model_k.ptr;
 	s.tri_n = t->tri_n.ptr;
 	s.model_xf = t->model_xf.ptr;
@@ -373,7 +375,7 @@ int srt_destroy(srt_tracer *t) {
 	cudaFree(t->sky);
 	t->shape_hdr.release(), t->shape_a.release(), t->shape_b.release(), t->model_xf.release(), t->materials.release();
 	t->bvh_nodes.release(), t->bvh_order.release(), t->bvh_root.release();
-	t->tri_aos.release(), t->tri_hot.release(), t->tri_flt.release(), t->model_k.release(), t->tri_n.release(), t->spans.release(), t->scratch.release();
+	t->tri_aos.release(), t->tri_hot.release(), t->tri_flt.release(), t->tri_uv.release(), t->model_k.release(), t->tri_n.release(), t->spans.release(), t->scratch.release();
 	if (t->stream) cudaStreamDestroy(t->stream);
 	delete t;
 	return SRT_OK;
@@ -437,6 +439,7 @@ int srt_upload_scene(srt_tracer *t, const srt_shape *shapes, size_t n_shapes, co
 	SRT_CUDA(t, t->tri_aos.reserve(6 * n_triangles));
 	SRT_CUDA(t, t->tri_hot.reserve(3 * soa));
 	SRT_CUDA(t, t->tri_flt.reserve(5 * soa + 2));
+	SRT_CUDA(t, t->tri_uv.reserve(5 * soa + 1));
 	SRT_CUDA(t, t->model_k.reserve(n_shapes));
 	SRT_CUDA(t, t->tri_n.reserve(3 * soa));
 	SRT_CUDA(t, t->spans.reserve(spans.size()));
@@ -458,9 +461,10 @@ int srt_upload_scene(srt_tracer *t, const srt_shape *shapes, size_t n_shapes, co
 		const int total = (int)soa;
 		SRT_CUDA(t, cudaMemsetAsync(t->model_k.ptr, 0, n_shapes * sizeof(float), st));
 		SRT_CUDA(t, cudaMemsetAsync(t->tri_flt.ptr, 0, (5 * soa + 2) * sizeof(float2), st));  // alignment gaps and the tail pad
+		SRT_CUDA(t, cudaMemsetAsync(t->tri_uv.ptr, 0, (5 * soa + 1) * sizeof(float4), st));
 		srt::prepare_triangles_kernel<<<(total + 255) / 256, 256, 0, st>>>(t->tri_aos.ptr, t->spans.ptr, (int)spans.size(), total,
 		                                                                  t->model_xf.ptr, t->tri_hot.ptr, t->tri_flt.ptr,
-		                                                                  t->model_k.ptr, t->tri_n.ptr);
+		                                                                  t->tri_uv.ptr, t->model_k.ptr, t->tri_n.ptr);
 		SRT_CUDA(t, cudaGetLastError());
 	}
 	SRT_CUDA(t, cudaStreamSynchronize(st));  // copy-in semantics, like the blocking writes of tracer.cpp:76-86
