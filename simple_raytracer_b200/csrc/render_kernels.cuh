@@ -63,6 +63,18 @@ struct DevScene {
 	float sun_dir[3];
 };
 
+// The first CONST_SHAPES shape records once more, as a KERNEL PARAMETER (constant bank): the closest-hit scan of a small
+// analytic scene walks the shape list with a warp-uniform index, so from here every record is a uniform constant-bank
+// load (LDCU) feeding uniform-register operands -- no per-lane address arithmetic, no LDG latency in the scan loop
+// (7 shapes x ~20 instructions of loop overhead per bounce on BASELINE config 2).  finish_hit keeps reading the global
+// arrays: its index differs from lane to lane.
+constexpr int CONST_SHAPES = 16;
+struct ShapeTable {
+	int4 hdr[CONST_SHAPES];
+	float4 a[CONST_SHAPES];
+	float4 b[CONST_SHAPES];
+};
+
 // A kernel launch covers `num_launches` consecutive launches of the reference's kernel `render` that differ in
 // nothing but `time` (srt_render_batch): one persistent grid pulls items of launch 0, then launch 1, ..., so the
 // ragged end of one launch -- the last long paths, and sweeps with only a few parked rays per warp -- is filled with
@@ -320,12 +332,12 @@ __device__ __noinline__ void bvh_traverse(const DevScene &sc, int root, vec3 o, 
 // resumes at index + 1.  Returns -1 when the scan reached the end of the list.
 // Normal / position of the winner are reconstructed afterwards (finish_hit) instead of at every
 // improvement; only the last improvement is observable.
-template <bool COUNT, bool PARK, bool MODELS = true, bool BVH = false>
+template <bool COUNT, bool PARK, bool MODELS = true, bool BVH = false, bool CONST = false>
 __device__ __forceinline__ int scan_shapes(const DevScene &sc, vec3 o, vec3 d, vec3 inv, int cursor, Hit &hit,
-                                           Counters &cnt) {
+                                           Counters &cnt, const ShapeTable *tab = nullptr) {
 	for (int i = cursor; i < sc.num_shapes; ++i) {
-		const int4 hdr = __ldg(&sc.shape_hdr[i]);
-		const float4 a = __ldg(&sc.shape_a[i]);
+		const int4 hdr = CONST ? tab->hdr[i] : __ldg(&sc.shape_hdr[i]);
+		const float4 a = CONST ? tab->a[i] : __ldg(&sc.shape_a[i]);
 		if (hdr.x == SHAPE_SPHERE) {
 			// intersect_sphere, :180-204
 			vec3 L = xyz(a) - o;
@@ -343,7 +355,7 @@ __device__ __forceinline__ int scan_shapes(const DevScene &sc, vec3 o, vec3 d, v
 			}
 		} else if (hdr.x == SHAPE_PLANE) {
 			// intersect_plane, :206-221
-			const float4 nb = __ldg(&sc.shape_b[i]);
+			const float4 nb = CONST ? tab->b[i] : __ldg(&sc.shape_b[i]);
 			vec3 n = xyz(nb);
 			float denom = dot(n, d);
 			if (fabsf(denom) != 0.0f) {
@@ -863,15 +875,17 @@ constexpr int BIG_SKYQ_BYTES = SRT_BIG_SKYQ ? (SRT_RENDER_THREADS / 32) * SKYQ_W
 // i.e. more resident warps for the latency-bound analytic path.
 // MODE_BVH (srt_set_accel(SRT_ACCEL_BVH), NOT the parity path) is the SMALL_MODELS machine with big models traversed
 // through their hierarchy inside the scan.
-enum { MODE_ANALYTIC = 0, MODE_SMALL_MODELS = 1, MODE_BIG_MODELS = 2, MODE_BVH = 3 };
+// MODE_ANALYTIC_CONST is MODE_ANALYTIC for scenes of at most CONST_SHAPES shapes, scanning the constant-bank table.
+enum { MODE_ANALYTIC = 0, MODE_SMALL_MODELS = 1, MODE_BIG_MODELS = 2, MODE_BVH = 3, MODE_ANALYTIC_CONST = 4 };
 template <bool COUNT, int MODE>
 __global__ void __launch_bounds__(RENDER_THREADS, MODE == MODE_BIG_MODELS ? SRT_MIN_BLOCKS : (MODE == MODE_BVH ? SRT_MIN_BLOCKS_BVH : SRT_MIN_BLOCKS_ANALYTIC))
 render_kernel(const __grid_constant__ RenderParams p, const __grid_constant__ DevScene sc,
-              float4 *__restrict__ scratch, unsigned long long *__restrict__ cursor, Counters *__restrict__ counters) {
+              const __grid_constant__ ShapeTable tab, float4 *__restrict__ scratch,
+              unsigned long long *__restrict__ cursor, Counters *__restrict__ counters) {
 	const unsigned FULL = 0xffffffffu;
 	const int lane = threadIdx.x & 31;
 	Counters cnt = {0, 0, 0, 0, 0, 0};
-	constexpr bool MODELS = MODE != MODE_ANALYTIC;   // the scan knows about model shapes
+	constexpr bool MODELS = MODE != MODE_ANALYTIC && MODE != MODE_ANALYTIC_CONST;  // the scan knows about model shapes
 	constexpr bool PHASES = MODE == MODE_BIG_MODELS;  // lanes park and the warp runs dense triangle phases
 	constexpr bool QUEUES = !PHASES;                  // dense camera-path batches through a warp queue
 	constexpr bool SKYQ = QUEUES || SRT_BIG_SKYQ;     // dense sky-box batches through a warp queue
@@ -1020,7 +1034,7 @@ render_kernel(const __grid_constant__ RenderParams p, const __grid_constant__ De
 				if (MODELS) inv = mk(rcp_(d.x), rcp_(d.y), rcp_(d.z));
 				scan_at = 0;
 			}
-			park = scan_shapes<COUNT, PHASES, MODELS, MODE == MODE_BVH>(sc, o, d, inv, scan_at, hit, cnt);
+			park = scan_shapes<COUNT, PHASES, MODELS, MODE == MODE_BVH, MODE == MODE_ANALYTIC_CONST>(sc, o, d, inv, scan_at, hit, cnt, &tab);
 
 			if (park < 0) {  // scan complete: shade this bounce, :404-468
 				scan_at = -1;

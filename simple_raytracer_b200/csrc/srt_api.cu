@@ -96,7 +96,8 @@ struct srt_tracer {
 	bool have_scene = false;
 
 	int band_h = 1, band_i = 0, band_n = 1;
-	int render_grid[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};  // [counted][mode]
+	int render_grid[2][5] = {{0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}};  // [counted][mode]
+	srt::ShapeTable shape_table{};  // the first CONST_SHAPES shape records, passed as a kernel parameter
 
 	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing;  // kernel launches since last query
 	uint64_t timed_launches = 0;                               // reference launches they cover (batches count each)
@@ -218,7 +219,7 @@ int launch_render_impl(srt_tracer *t, const srt::RenderParams &p) {
 	}
 	const srt::DevScene sc = dev_scene(t);
 	cudaError_t le = cudaEventRecord(ev.first, t->stream);
-	kernel<<<grid, srt::RENDER_THREADS, smem, t->stream>>>(p, sc, t->scratch.ptr, t->cursor, t->counters);
+	kernel<<<grid, srt::RENDER_THREADS, smem, t->stream>>>(p, sc, t->shape_table, t->scratch.ptr, t->cursor, t->counters);
 	srt::accumulate_kernel<<<(p.total_pixels + 255) / 256, 256, 0, t->stream>>>(p, t->scratch.ptr, t->canvas);
 	if (le == cudaSuccess) le = cudaEventRecord(ev.second, t->stream);
 	if (le == cudaSuccess) le = cudaGetLastError();
@@ -238,6 +239,7 @@ int launch_render_impl(srt_tracer *t, const srt::RenderParams &p) {
 
 template <bool COUNT>
 int launch_params(srt_tracer *t, const srt::RenderParams &p) {
+	if (!t->has_models && t->n_shapes <= (size_t)srt::CONST_SHAPES) return launch_render_impl<COUNT, srt::MODE_ANALYTIC_CONST>(t, p);
 	if (!t->has_models) return launch_render_impl<COUNT, srt::MODE_ANALYTIC>(t, p);
 	if (t->accel == SRT_ACCEL_BVH && t->bvh_ready && t->has_big_models) return launch_render_impl<COUNT, srt::MODE_BVH>(t, p);
 	if (!t->has_big_models) return launch_render_impl<COUNT, srt::MODE_SMALL_MODELS>(t, p);
@@ -476,6 +478,9 @@ int srt_upload_scene(srt_tracer *t, const srt_shape *shapes, size_t n_shapes, co
 	t->scene_data = *scene_data;
 	t->scene_data.num_shapes = (int)n_shapes;  // tracer.cpp:94
 	t->host_hdr = hdr;
+	t->shape_table = srt::ShapeTable{};
+	for (size_t i = 0; i < std::min<size_t>(n_shapes, srt::CONST_SHAPES); ++i)
+		t->shape_table.hdr[i] = hdr[i], t->shape_table.a[i] = a[i], t->shape_table.b[i] = b[i];
 	t->bvh_ready = false;
 	t->have_scene = true;
 	if (t->accel == SRT_ACCEL_BVH) return build_bvh(t);
