@@ -114,6 +114,10 @@ struct Hit {
 #define SRT_PHASE_PATIENCE 1
 #endif
 constexpr int PHASE_PATIENCE = SRT_PHASE_PATIENCE;
+#ifndef SRT_SHADE_SYNC  // lanes ready to shade wait for parked ones unless this many are ready (0 = never wait: the default)
+#define SRT_SHADE_SYNC 0
+#endif
+constexpr int SHADE_SYNC = SRT_SHADE_SYNC;
 // Models with at most this many triangles are intersected inline during the shape scan; larger
 // ones park the lane until the warp runs a dense triangle phase (see render_kernel).
 constexpr int INLINE_MODEL_TRIS = 32;
@@ -916,6 +920,7 @@ render_kernel(const __grid_constant__ RenderParams p, const __grid_constant__ De
 	Hit hit = {0.f, -1, -1};
 	int scan_at = -1;  // next shape to visit; -1 = a new bounce has to be started
 	int park = -1;     // shape index of the model this lane waits to run triangles for
+	bool ready = false;  // the scan of the current bounce is complete: the lane waits to shade it
 	int waited = 0;    // warp-uniform: trips spent with parked lanes waiting for company
 	// warp-uniform queue state (QUEUES builds)
 	uint32_t *rayq = reinterpret_cast<uint32_t *>(smem_raw + warp * QUEUE_WARP_BYTES);
@@ -1025,7 +1030,7 @@ render_kernel(const __grid_constant__ RenderParams p, const __grid_constant__ De
 		if (!__any_sync(FULL, alive)) break;
 
 		bool push_sky = false;
-		if (alive && park < 0) {
+		if (alive && park < 0 && !ready) {
 			if (scan_at < 0) {  // new bounce: closest_intersection prologue, :294-297
 				if (COUNT) cnt.bounces += 1;
 				hit.t = __int_as_float(0x7f800000);
@@ -1035,9 +1040,26 @@ render_kernel(const __grid_constant__ RenderParams p, const __grid_constant__ De
 				scan_at = 0;
 			}
 			park = scan_shapes<COUNT, PHASES, MODELS, MODE == MODE_BVH, MODE == MODE_ANALYTIC_CONST>(sc, o, d, inv, scan_at, hit, cnt, &tab);
-
-			if (park < 0) {  // scan complete: shade this bounce, :404-468
+			if (park < 0) {  // scan complete
 				scan_at = -1;
+				ready = true;
+			}
+		}
+		// Shading.  A lane shades in the trip its scan completes.  With dense triangle phases lanes finish their scans at
+		// different trips (they park at different models), so hit shading runs at ~11 of 32 lanes on the two-mesh config.
+		// SHADE_SYNC > 0 makes ready lanes WAIT while any lane is still parked unless that many are ready (phases first,
+		// then a nearly full warp shades).  Measured: 20 / 28 / 33 -> +0 / -1 / -5 % on config 3, -2 / -3 / -7 % on
+		// config 5 -- waiting lanes delay the NEXT bounce's parked rays, and thinner phases cost more than fuller
+		// shading saves -- so it is off; the flattened "everybody advances when it can" schedule stays.
+		bool shade_now = true;
+		if (PHASES && SHADE_SYNC > 0) {
+			const unsigned rd = __ballot_sync(FULL, ready);
+			const unsigned pk = __ballot_sync(FULL, park >= 0);
+			shade_now = pk == 0u || __popc(rd) >= SHADE_SYNC;
+		}
+		if (ready && shade_now) {  // shade this bounce, :404-468
+			ready = false;
+			{
 				bool done;
 				if (hit.shape >= 0) {
 					if (COUNT) cnt.hits += 1;
@@ -1101,7 +1123,7 @@ render_kernel(const __grid_constant__ RenderParams p, const __grid_constant__ De
 		// for company; parked lanes get back to tracing as soon as possible.
 		const unsigned parked = PHASES ? __ballot_sync(FULL, park >= 0) : 0u;
 		if (PHASES && parked) {
-			const unsigned movable = __ballot_sync(FULL, alive && park < 0);
+			const unsigned movable = __ballot_sync(FULL, alive && park < 0 && !ready);
 			if (movable == 0 || waited >= PHASE_PATIENCE) {
 				// the model most lanes wait for (ties: the lower shape index)
 				const unsigned same = __match_any_sync(FULL, park);
