@@ -72,7 +72,10 @@ int main(int argc, char **argv) {
 		return 0;
 	}
 
-	Tracer tracer(width, height, sky.data(), sw, sh);
+	// With SRT_SKYBOX_PNG=<file> the tracer decodes the sky box itself, as the reference's constructor does with
+	// "assets/skybox.png" (tracer.cpp:42-52); otherwise the procedural texels above are handed over.
+	const char *sky_png = std::getenv("SRT_SKYBOX_PNG");
+	Tracer tracer = sky_png ? Tracer(width, height, std::string(sky_png)) : Tracer(width, height, sky.data(), sw, sh);
 	tracer.options.num_samples = 2;   // src/main.cpp:116-118
 	tracer.options.num_bounces = 10;
 	tracer.options.show_normals = false;

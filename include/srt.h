@@ -194,6 +194,11 @@ int srt_load_stl(const char *path, srt_triangle **triangles, size_t *count);
 int srt_load_obj(const char *path, srt_triangle **triangles, size_t *count);
 int srt_save_ppm(const char *path, const uint8_t *argb, int width, int height);
 void srt_free(void *p);
+/* The sky-box image as Tracer::Tracer prepares it (reference src/tracer.cpp:42-52: stbi_set_flip_vertically_on_load(1),
+ * stbi_loadf_from_file(..., 4)): an 8-bit PNG decoded to width*height RGBA float32 texels, memory row 0 = image bottom,
+ * colour = (float)pow(x / 255.0f, 2.2f), alpha = x / 255.0f (lib/stb_image.h:1868-1874).  The array is what srt_create
+ * takes; free it with srt_free.  8-bit grey / grey+alpha / RGB / RGBA / palette PNGs, non-interlaced. */
+int srt_load_skybox_png(const char *path, float **rgba, int *width, int *height);
 /* Model::compute_bounding_box, reference src/shape.cpp:45-58 */
 int srt_model_bounds(const srt_triangle *triangles, size_t n_triangles, srt_model *model);
 

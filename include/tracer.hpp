@@ -42,6 +42,21 @@ class Tracer {
 		if (srt_create(width, height, skybox_rgba, sky_w, sky_h, device, &handle_) != SRT_OK)
 			throw std::runtime_error(std::string("srt_create: ") + srt_last_error(nullptr));
 	}
+	// Tracer::Tracer(width, height) as the reference writes it: the constructor decodes the sky-box PNG itself
+	// (tracer.cpp:42-45 opens "assets/skybox.png"; the path is an argument here, with that default).
+	Tracer(int width, int height, const std::string &skybox_png = "assets/skybox.png", int device = -1) {
+		options.width = width;
+		options.height = height;
+		options.num_samples = 4;
+		options.num_bounces = 10;
+		float *sky = nullptr;
+		int sw = 0, sh = 0;
+		if (srt_load_skybox_png(skybox_png.c_str(), &sky, &sw, &sh) != SRT_OK)
+			throw std::runtime_error("Tracer: cannot read the sky box " + skybox_png);
+		const int rc = srt_create(width, height, sky, sw, sh, device, &handle_);
+		srt_free(sky);
+		if (rc != SRT_OK) throw std::runtime_error(std::string("srt_create: ") + srt_last_error(nullptr));
+	}
 	~Tracer() { srt_destroy(handle_); }
 	Tracer(const Tracer &) = delete;
 	Tracer &operator=(const Tracer &) = delete;

@@ -7,5 +7,5 @@ mkdir -p ../../build/variants
 NV="/usr/local/cuda/bin/nvcc -std=c++17 -O3 -gencode arch=compute_100a,code=sm_100a -lineinfo --fmad=false -prec-div=true -prec-sqrt=true -ftz=false -Xcompiler -fPIC,-ffp-contract=off"
 $NV $flags -c -o /tmp/srt_api_$name.o srt_api.cu
 [ -f mesh_io.o ] || g++ -std=c++17 -O2 -fPIC -ffp-contract=off -c -o mesh_io.o mesh_io.cpp
-/usr/local/cuda/bin/nvcc -shared -gencode arch=compute_100a,code=sm_100a -o ../../build/variants/libsrt_$name.so /tmp/srt_api_$name.o mesh_io.o
+/usr/local/cuda/bin/nvcc -shared -gencode arch=compute_100a,code=sm_100a -o ../../build/variants/libsrt_$name.so /tmp/srt_api_$name.o mesh_io.o -lz
 echo built build/variants/libsrt_$name.so

@@ -19,6 +19,8 @@
 #include <string>
 #include <vector>
 
+#include <zlib.h>
+
 #include "../../include/srt.h"
 
 namespace {
@@ -255,6 +257,113 @@ int srt_save_ppm(const char *path, const uint8_t *argb, int width, int height) {
 	if (!path || !argb || width <= 0 || height <= 0) return SRT_ERR_INVALID;
 	try {
 		return save_ppm(path, argb, width, height);
+	} catch (const std::exception &) {
+		return SRT_ERR_INVALID;
+	}
+}
+
+// ---- sky-box image: PNG -> RGBA float32 the way the reference prepares it (src/tracer.cpp:42-52) --------------------
+// stbi_set_flip_vertically_on_load(1) + stbi_loadf_from_file(..., 4): the 8-bit image is expanded to 4 channels, rows
+// bottom-up, colour = (float)pow(x / 255.0f, 2.2f) evaluated in double, alpha = x / 255.0f (lib/stb_image.h:1868-1874).
+// stb_image is the reference's vendored third-party code and is not copied: this is a small PNG reader of its own
+// (8-bit grey / grey+alpha / RGB / RGBA / palette, non-interlaced -- what image editors write), zlib does the inflate.
+static uint32_t be32(const uint8_t *p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
+
+static int load_skybox_png(const char *path, float **rgba, int *width, int *height) {
+	FILE *f = fopen(path, "rb");
+	if (!f) return SRT_ERR_INVALID;
+	std::vector<uint8_t> file;
+	uint8_t buf[65536];
+	for (size_t n; (n = fread(buf, 1, sizeof buf, f)) > 0;) file.insert(file.end(), buf, buf + n);
+	fclose(f);
+	static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+	if (file.size() < 8 + 25 || memcmp(file.data(), sig, 8) != 0) return SRT_ERR_INVALID;
+	uint32_t w = 0, h = 0;
+	int depth = 0, ctype = -1, interlace = 0;
+	std::vector<uint8_t> idat, palette, trns;
+	for (size_t at = 8; at + 12 <= file.size();) {
+		const uint32_t len = be32(&file[at]);
+		const uint8_t *type = &file[at + 4], *data = &file[at + 8];
+		if (len > file.size() - at - 12) return SRT_ERR_INVALID;
+		if (!memcmp(type, "IHDR", 4) && len == 13) {
+			w = be32(data), h = be32(data + 4), depth = data[8], ctype = data[9], interlace = data[12];
+		} else if (!memcmp(type, "PLTE", 4)) {
+			palette.assign(data, data + len);
+		} else if (!memcmp(type, "tRNS", 4)) {
+			trns.assign(data, data + len);
+		} else if (!memcmp(type, "IDAT", 4)) {
+			idat.insert(idat.end(), data, data + len);
+		} else if (!memcmp(type, "IEND", 4)) {
+			break;
+		}
+		at += 12 + (size_t)len;
+	}
+	const int channels = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 3 ? 1 : ctype == 4 ? 2 : ctype == 6 ? 4 : 0;
+	if (!w || !h || w > 32768 || h > 32768 || depth != 8 || !channels || interlace || idat.empty()) return SRT_ERR_INVALID;
+	if (ctype == 3 && palette.size() < 3) return SRT_ERR_INVALID;
+	const size_t stride = (size_t)w * channels;
+	std::vector<uint8_t> raw((stride + 1) * h);
+	uLongf raw_len = (uLongf)raw.size();
+	if (uncompress(raw.data(), &raw_len, idat.data(), (uLong)idat.size()) != Z_OK || raw_len != raw.size()) return SRT_ERR_INVALID;
+	// undo the per-row filters (PNG specification, section 9), in place over a zero row above the first
+	std::vector<uint8_t> img(stride * h), zero(stride, 0);
+	for (uint32_t y = 0; y < h; ++y) {
+		const uint8_t *in = &raw[(stride + 1) * y];
+		uint8_t *out = &img[stride * y];
+		const uint8_t *up = y ? out - stride : zero.data();
+		const int ft = in[0];
+		if (ft > 4) return SRT_ERR_INVALID;
+		for (size_t i = 0; i < stride; ++i) {
+			const int a = i >= (size_t)channels ? out[i - channels] : 0, b = up[i], c = i >= (size_t)channels ? up[i - channels] : 0;
+			int pred = 0;
+			if (ft == 1) pred = a;
+			else if (ft == 2) pred = b;
+			else if (ft == 3) pred = (a + b) >> 1;
+			else if (ft == 4) {
+				const int p = a + b - c, pa = abs(p - a), pb = abs(p - b), pc = abs(p - c);
+				pred = (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
+			}
+			out[i] = (uint8_t)(in[1 + i] + pred);
+		}
+	}
+	float lut[256], lin[256];
+	for (int i = 0; i < 256; ++i) {
+		lut[i] = (float)pow((double)(i / 255.0f), (double)2.2f);  // stbi__ldr_to_hdr, lib/stb_image.h:1868
+		lin[i] = i / 255.0f;
+	}
+	float *px = static_cast<float *>(malloc((size_t)w * h * 4 * sizeof(float)));
+	if (!px) return SRT_ERR_INVALID;
+	for (uint32_t y = 0; y < h; ++y) {
+		const uint8_t *row = &img[stride * y];
+		float *dst = px + (size_t)(h - 1 - y) * w * 4;  // memory row 0 = image bottom (flip on load)
+		for (uint32_t x = 0; x < w; ++x) {
+			uint8_t r, g, b, a = 255;
+			if (ctype == 0) r = g = b = row[x];
+			else if (ctype == 4) r = g = b = row[2 * x], a = row[2 * x + 1];
+			else if (ctype == 2) r = row[3 * x], g = row[3 * x + 1], b = row[3 * x + 2];
+			else if (ctype == 6) r = row[4 * x], g = row[4 * x + 1], b = row[4 * x + 2], a = row[4 * x + 3];
+			else {
+				const size_t k = row[x];
+				if (3 * k + 2 >= palette.size()) {
+					free(px);
+					return SRT_ERR_INVALID;
+				}
+				r = palette[3 * k], g = palette[3 * k + 1], b = palette[3 * k + 2];
+				if (k < trns.size()) a = trns[k];
+			}
+			dst[4 * x] = lut[r], dst[4 * x + 1] = lut[g], dst[4 * x + 2] = lut[b], dst[4 * x + 3] = lin[a];
+		}
+	}
+	*rgba = px, *width = (int)w, *height = (int)h;
+	return SRT_OK;
+}
+
+int srt_load_skybox_png(const char *path, float **rgba, int *width, int *height) {
+	if (!path || !rgba || !width || !height) return SRT_ERR_INVALID;
+	*rgba = nullptr;
+	*width = *height = 0;
+	try {
+		return load_skybox_png(path, rgba, width, height);
 	} catch (const std::exception &) {
 		return SRT_ERR_INVALID;
 	}

@@ -70,6 +70,7 @@ def load_library():
         "srt_load_obj": [ctypes.c_char_p, pp, ctypes.POINTER(sz)],
         "srt_save_ppm": [ctypes.c_char_p, vp, i32, i32],
         "srt_model_bounds": [vp, sz, vp],
+        "srt_load_skybox_png": [ctypes.c_char_p, pp, ctypes.POINTER(i32), ctypes.POINTER(i32)],
     }
     for name, args in sigs.items():
         fn = getattr(L, name)
@@ -297,6 +298,20 @@ def load_obj_model(path, triangles):
         return None
     first = len(triangles)
     return (first, len(new)), concat_records(TRIANGLE, triangles, new)
+
+
+def load_skybox_png(path):
+    """srt_load_skybox_png: the (h, w, 4) float32 array Tracer(width, height, skybox) takes, decoded from a PNG the way
+    the reference's constructor does (src/tracer.cpp:42-52).  None if the file cannot be read."""
+    L = load_library()
+    ptr, w, h = ctypes.c_void_p(), ctypes.c_int(), ctypes.c_int()
+    if L.srt_load_skybox_png(os.fsencode(path), ctypes.byref(ptr), ctypes.byref(w), ctypes.byref(h)):
+        return None
+    try:
+        buf = (ctypes.c_float * (w.value * h.value * 4)).from_address(ptr.value)
+        return np.frombuffer(buf, np.float32).reshape(h.value, w.value, 4).copy()
+    finally:
+        L.srt_free(ptr)
 
 
 def save_ppm(path, pixels, width, height):

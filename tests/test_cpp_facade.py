@@ -84,8 +84,9 @@ def test_cpp_scene_helpers_build_the_same_bytes_as_the_python_mirror(tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("with_mesh", [False, True])
-def test_headless_harness_matches_python_path_and_oracle(tmp_path, oracle_lib, with_mesh):
+@pytest.mark.parametrize("with_mesh,png_sky", [(False, False), (True, False), (True, True)])
+def test_headless_harness_matches_python_path_and_oracle(tmp_path, oracle_lib, with_mesh, png_sky):
+    from simple_raytracer_b200 import tracer as tracer_mod
     from simple_raytracer_b200.tracer import Tracer
     build_harness()
     w, h, frames = 200, 120, 3
@@ -95,7 +96,14 @@ def test_headless_harness_matches_python_path_and_oracle(tmp_path, oracle_lib, w
     if with_mesh:  # "Add model" through load_stl_model + Model(triangles, first, count)
         path, mesh = _mesh_file(tmp_path)
         args.append(str(path))
-    subprocess.check_call(args)
+    env = dict(os.environ)
+    if png_sky:  # Tracer(width, height, "sky.png"): the facade decodes the sky box itself, like the reference's constructor
+        from PIL import Image
+        yy, xx = np.mgrid[0:48, 0:96]
+        img = np.stack([60 + yy * 3, 90 + (xx + yy) % 120, 140 + yy * 2], -1).astype(np.uint8)
+        Image.fromarray(img, "RGB").save(tmp_path / "sky.png")
+        env["SRT_SKYBOX_PNG"] = str(tmp_path / "sky.png")
+    subprocess.check_call(args, env=env)
     data = out.read_bytes()
     header = f"P6 {w} {h} 255\n".encode()
     assert data.startswith(header)
@@ -106,6 +114,8 @@ def test_headless_harness_matches_python_path_and_oracle(tmp_path, oracle_lib, w
     sky = np.ones((32, 64, 4), F)
     v = ((np.arange(32, dtype=F) + F(0.5)) / F(32))[:, None]
     sky[..., 0], sky[..., 1], sky[..., 2] = F(0.25) + F(0.3) * v, F(0.35) + F(0.35) * v, F(0.5) + F(0.45) * v
+    if png_sky:
+        sky = tracer_mod.load_skybox_png(env["SRT_SKYBOX_PNG"])
     sc = _mirror_scene(w, h, frames, mesh)
     tr = Tracer(w, h, sky)
     tr.scene_data[:] = sc.scene_data
