@@ -161,6 +161,11 @@ enum { SRT_ACCEL_NONE = 0, SRT_ACCEL_BVH = 1 };
 int srt_set_accel(srt_tracer *t, int accel);
 
 /* Harness / test entry points (no reference counterpart). */
+/* Which conservative filter the dense triangle sweep runs before the exact test (results are bit-identical either
+ * way; only the speed differs): AUTO = two-strip (u and v ranges) for models of at most 20000 triangles, one-strip
+ * (u range) above; the other two force one kind for every model (parity tests run both, tuning). */
+enum { SRT_FILTER_AUTO = 0, SRT_FILTER_ONE_STRIP = 1, SRT_FILTER_TWO_STRIP = 2 };
+int srt_set_sweep_filter(srt_tracer *t, int mode);
 int srt_read_canvas(srt_tracer *t, float *rgba_out);               /* width*height*4 floats; synchronises */
 int srt_write_canvas(srt_tracer *t, const float *rgba_in);         /* restore an accumulation (checkpoint/resume) */
 int srt_canvas_device_ptr(srt_tracer *t, void **ptr, size_t *bytes); /* for NCCL reduce of per-GPU canvases */

@@ -98,6 +98,7 @@ struct RenderParams {
 	unsigned int total_pixels; // my_rows * width
 	unsigned int total_items;  // num_launches * items_per_launch: item = (launch * total_pixels + local_pixel) * num_samples + sample
 	float inv_ns;              // 1/num_samples when that is exact (num_samples a power of two), else 0
+	int uv_max_tris;           // models of at most this many triangles are swept with the two-strip filter
 };
 
 struct Counters {
@@ -1132,7 +1133,7 @@ render_kernel(const __grid_constant__ RenderParams p, const __grid_constant__ De
 				const int model = 0xfffff - (best & 0xfffff);
 				const int4 hdr = __ldg(&sc.shape_hdr[model]);
 				const bool active = park == model;
-				if (hdr.w <= UV_MAX_TRIS)  // few, large triangles: the two-strip filter pays for itself (warp-uniform)
+				if (hdr.w <= p.uv_max_tris)  // few, large triangles: the two-strip filter pays for itself (warp-uniform)
 					triangle_phase<true>(sc, hdr.w, hdr.z, model, active, o, d, hit, wsmem, wsmem_s, bars_s, parity, lane);
 				else
 					triangle_phase<false>(sc, hdr.w, hdr.z, model, active, o, d, hit, wsmem, wsmem_s, bars_s, parity, lane);

@@ -96,6 +96,7 @@ struct srt_tracer {
 	bool have_scene = false;
 
 	int band_h = 1, band_i = 0, band_n = 1;
+	int uv_max_tris = srt::UV_MAX_TRIS;  // srt_set_sweep_filter
 	int render_grid[2][5] = {{0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}};  // [counted][mode]
 	srt::ShapeTable shape_table{};  // the first CONST_SHAPES shape records, passed as a kernel parameter
 
@@ -178,6 +179,7 @@ int make_params(srt_tracer *t, const srt_render_data *rd, srt::RenderParams &p) 
 	p.num_launches = 1;
 	p.times[0] = rd->time;
 	p.inv_ns = (rd->num_samples & (rd->num_samples - 1)) == 0 ? 1.0f / (float)rd->num_samples : 0.0f;
+	p.uv_max_tris = t->uv_max_tris;
 	p.band_h = t->band_h;
 	p.band_i = t->band_i;
 	p.band_n = t->band_n;
@@ -662,6 +664,15 @@ int srt_set_row_bands(srt_tracer *t, int band_height, int band_index, int band_c
 	}
 	if (band_height < 1 || band_index < 0 || band_index >= band_count) return fail(t, SRT_ERR_INVALID, "bad row bands");
 	t->band_h = band_height, t->band_i = band_index, t->band_n = band_count;
+	return SRT_OK;
+}
+
+int srt_set_sweep_filter(srt_tracer *t, int mode) {
+	if (!t) return SRT_ERR_INVALID;
+	if (mode == SRT_FILTER_AUTO) t->uv_max_tris = srt::UV_MAX_TRIS;
+	else if (mode == SRT_FILTER_ONE_STRIP) t->uv_max_tris = -1;
+	else if (mode == SRT_FILTER_TWO_STRIP) t->uv_max_tris = 0x7fffffff;
+	else return fail(t, SRT_ERR_INVALID, "unknown sweep filter %d", mode);
 	return SRT_OK;
 }
 

@@ -50,6 +50,7 @@ def load_library():
         "srt_render_frame": [vp, vp, u32, vp],
         "srt_set_row_bands": [vp, i32, i32, i32],
         "srt_set_accel": [vp, i32],
+        "srt_set_sweep_filter": [vp, i32],
         "srt_read_canvas": [vp, vp],
         "srt_write_canvas": [vp, vp],
         "srt_canvas_device_ptr": [vp, pp, ctypes.POINTER(sz)],
@@ -116,6 +117,8 @@ class Tracer:
         self.options["width"], self.options["height"] = self.width, self.height
         self.options["num_samples"], self.options["num_bounces"] = 4, 10
         self.scene_data = np.zeros(1, SCENE_DATA)
+        if os.environ.get("SRT_SWEEP_FILTER"):  # test / tuning hook: "auto", "one", "two" (bit-identical results)
+            self.set_sweep_filter(os.environ["SRT_SWEEP_FILTER"])
 
     # -- reference surface ----------------------------------------------------------------------
     def update_scene(self, shapes, triangles, materials):
@@ -197,6 +200,10 @@ class Tracer:
         """srt_set_accel: "none" (default: the reference's brute-force triangle loop, bit-exact) or "bvh" (labelled
         extension outside the parity path)."""
         self._check(self._lib.srt_set_accel(self._h, {"none": 0, "bvh": 1}[accel]))
+
+    def set_sweep_filter(self, mode):
+        """srt_set_sweep_filter: "auto" | "one" | "two" -- which conservative filter precedes the exact triangle test."""
+        self._check(self._lib.srt_set_sweep_filter(self._h, {"auto": 0, "one": 1, "two": 2}[mode]))
 
     def read_canvas(self):
         out = np.empty((self.height, self.width, 4), np.float32)

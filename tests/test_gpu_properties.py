@@ -11,6 +11,15 @@ from util import cuda_canvas, make_tracer, psnr
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=["one", "two"])
+def sweep_filter(request, monkeypatch):
+    """Run a mesh test under BOTH conservative sweep filters (srt_set_sweep_filter through the Tracer's
+    SRT_SWEEP_FILTER hook): the one-strip filter big models get and the two-strip filter small models get must each
+    reproduce the reference bit for bit on every adversarial mesh, whatever the size-based default would pick."""
+    monkeypatch.setenv("SRT_SWEEP_FILTER", request.param)
+    return request.param
+
+
 def test_row_bands_partition_is_bit_identical_at_1080p(sky):
     """Tile sharding invariant at config-2 size: the union of 8 interleaved band renders == the full frame."""
     sc = scenes.config2()
@@ -49,7 +58,7 @@ def test_accumulation_linearity_and_determinism_full_size(sky):
     assert (~np.isfinite(acc)).sum() <= 12
 
 
-def test_mesh_config_full_size_against_oracle_crop(sky, oracle_lib):
+def test_mesh_config_full_size_against_oracle_crop(sky, oracle_lib, sweep_filter):
     """Config 3 at 1080p: the CUDA frame equals the oracle on a centred 240x136 window of the same
     full-size launch (global pixel ids, seeds and aspect preserved)."""
     sc = scenes.config3()
@@ -64,7 +73,7 @@ def test_mesh_config_full_size_against_oracle_crop(sky, oracle_lib):
     assert (want[y0:y0 + 136, x0:x0 + 240, :3] > 0).any()
 
 
-def test_stress_mesh_primary_and_crop(sky, oracle_lib):
+def test_stress_mesh_primary_and_crop(sky, oracle_lib, sweep_filter):
     """Config 5 (100 352 triangles): primary ids / t and 1-spp radiance on a crop against the oracle."""
     sc = scenes.config5(480, 270)
     tr = make_tracer(sc, sky)
@@ -171,7 +180,7 @@ def test_ragged_sizes_and_sample_counts(sky, oracle_lib):
         assert_bit_equal(want, tr.read_canvas(), f"{w}x{h} ns={ns} nb={nb}")
 
 
-def test_shared_triangles_between_instances_and_empty_model(sky, oracle_lib):
+def test_shared_triangles_between_instances_and_empty_model(sky, oracle_lib, sweep_filter):
     """Several box models share the 12 cube triangles (shape.cpp:76-89); a model with zero triangles is legal."""
     tris = scenes.cube_triangles()
     mats = np.zeros(3, scenes.MATERIAL)
@@ -215,7 +224,7 @@ def _random_mesh(rng, n_tris, center, extent):
 
 
 @pytest.mark.parametrize("sizes", [(33,), (127, 128, 129), (32, 257, 31, 1000, 64), (513, 40, 40, 40, 700, 33)])
-def test_models_of_awkward_sizes_tile_boundaries_and_many_instances(sky, oracle_lib, sizes):
+def test_models_of_awkward_sizes_tile_boundaries_and_many_instances(sky, oracle_lib, sizes, sweep_filter):
     """Triangle-phase bookkeeping: tile tails (n mod 128), the inline/parked threshold (32 / 33 triangles),
     more distinct big models than a warp sweeps at once, duplicate and degenerate triangles, instances."""
     rng = np.random.default_rng(sum(sizes))
@@ -263,7 +272,7 @@ def test_models_of_awkward_sizes_tile_boundaries_and_many_instances(sky, oracle_
     assert len(set(np.unique(gi))) >= min(len(sizes), 3)
 
 
-def test_rays_through_shared_edges_and_vertices(sky, oracle_lib):
+def test_rays_through_shared_edges_and_vertices(sky, oracle_lib, sweep_filter):
     """Adversarial for the triangle filter: a regular grid of rays (time = 0 gives every pixel the same jitter)
     against an axis-aligned triangle grid, so many rays pass within rounding distance of shared edges and
     vertices (u, v near 0 or 1), plus the same grid seen almost edge-on (det near 0, grazing rays)."""
@@ -316,7 +325,7 @@ def _check_against_oracle(sc, sky, oracle_lib, what, min_mesh_pixels=200, mesh_s
 
 
 @pytest.mark.parametrize("offset", [(0, 0, 0), (1000.0, -2000.0, 512.0), (-3.0e5, 1.0e5, 2.0e5)])
-def test_sweep_filter_margins_far_from_the_origin(sky, oracle_lib, offset):
+def test_sweep_filter_margins_far_from_the_origin(sky, oracle_lib, offset, sweep_filter):
     """The sweep filter works on pre-multiplied operands (o x d, e2 x v0) whose rounding error grows with the
     distance from the origin; its margins must grow with it.  The same mesh and camera translated far away: the
     reference's own arithmetic degrades there (o - v0 loses bits), and the CUDA path must degrade identically."""
@@ -330,7 +339,7 @@ def test_sweep_filter_margins_far_from_the_origin(sky, oracle_lib, offset):
 
 
 @pytest.mark.parametrize("size", [1e-4, 1e-2, 1e3])
-def test_sweep_filter_tiny_and_huge_triangles(sky, oracle_lib, size):
+def test_sweep_filter_tiny_and_huge_triangles(sky, oracle_lib, size, sweep_filter):
     """Mesh scale from 1e-4 to 1e3 scene units (the absolute 2e-6 slack of the filter dominates at the small end,
     the relative terms at the large end); the camera distance scales along."""
     v, n, f = scenes.noisy_icosphere(2, seed=4)
@@ -339,7 +348,7 @@ def test_sweep_filter_tiny_and_huge_triangles(sky, oracle_lib, size):
     _check_against_oracle(sc, sky, oracle_lib, f"size {size}")
 
 
-def test_sweep_filter_undecidable_triangles_overflow_the_pair_ring(sky, oracle_lib):
+def test_sweep_filter_undecidable_triangles_overflow_the_pair_ring(sky, oracle_lib, sweep_filter):
     """Hundreds of zero-area triangles (all three vertices equal, or collinear): det = 0, so the filter can decide
     nothing and every one of them survives -- far more survivors per tile than the pair ring holds -- while the
     reference rejects them all (render.cl:253).  Real triangles are interleaved so that hits still have to be
@@ -360,7 +369,7 @@ def test_sweep_filter_undecidable_triangles_overflow_the_pair_ring(sky, oracle_l
     _check_against_oracle(sc, sky, oracle_lib, "junk triangles")
 
 
-def test_sweep_filter_nan_and_inf_operands(sky, oracle_lib):
+def test_sweep_filter_nan_and_inf_operands(sky, oracle_lib, sweep_filter):
     """A model containing triangles with NaN / inf coordinates, and an AABB that lets every ray in: the filter must
     pass what it cannot decide, and the exact test then behaves as the reference does."""
     v, n, f = scenes.noisy_icosphere(2, seed=8)
