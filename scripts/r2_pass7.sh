@@ -1,0 +1,9 @@
+#!/bin/bash
+mkdir -p gpurun_out
+python -m pytest tests -m gpu -q -x 2>&1 | tail -4
+for fb in 1 2 4; do
+  echo "== SRT_FRAME_BANDS=$fb"
+  SRT_FRAME_BANDS=$fb python bench.py --steps 10 --no-cpu-baseline --no-extras 2>/dev/null | python -c "
+import sys, json
+j = json.loads(sys.stdin.read()); print('value %.1f  e2e %.1f' % (j['value'], j['e2e']['value']))"
+done | tee gpurun_out/r2i_frame_bands.txt

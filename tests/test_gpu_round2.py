@@ -202,3 +202,29 @@ def test_failed_upload_keeps_the_handle_consistent(sky):
     rd["width"] = 199
     with pytest.raises(SrtError):
         tr.accumulate(rd)
+
+
+@pytest.mark.parametrize("cfg,w,h", [(2, 1920, 1080), (3, 1000, 701), (1, 800, 600)])
+@pytest.mark.parametrize("pinned", [False, True])
+def test_frame_call_equals_render_then_resolve_at_full_size(sky, cfg, w, h, pinned):
+    """Tracer.render (srt_render_frame: render + average + blocking read-back in one call, tracer.cpp:103-116) at full
+    frame sizes: canvas and ARGB8 image are exactly those of srt_render + srt_resolve -- analytic, small-model and
+    dense-sweep kernel builds, an odd height, accumulation over several frames, staged and page-locked outputs."""
+    sc = scenes.CONFIGS[cfg](w, h)
+    tr = make_tracer(sc, sky)
+    out = np.zeros((h, w, 4), np.uint8)
+    if pinned:
+        tr.pin_output(out)
+    tr.clear_canvas()
+    for k in range(3):
+        tr.options[:] = sc.render_data(k, num_samples=2)
+        tr.render(k + 1, out.reshape(-1))
+    got_canvas, got_img = tr.read_canvas(), out.copy()
+    if pinned:
+        tr.unpin_output()
+    tr.clear_canvas()
+    for k in range(3):
+        tr.accumulate(sc.render_data(k, num_samples=2))
+    assert_bit_equal(tr.read_canvas(), got_canvas, "canvas after three pipelined frames")
+    assert np.array_equal(tr.resolve(3), got_img)
+    assert got_img[..., 0].min() == 255 and got_img[..., 1:].any()
