@@ -1,3 +1,3 @@
 #!/bin/bash
 mkdir -p gpurun_out
-scripts/ncu_capture.sh 3 r2g_prof_c3 2
+scripts/ncu_capture.sh 2 r2j_prof_c2 16 - batch

@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-python -m pytest tests/test_gpu_parity.py tests/test_gpu_properties.py -q -x 2>&1 | tail -3
+python -m pytest tests -m gpu -q -x 2>&1 | tail -3
 for lib in build/variants/libsrt_*.so; do
   echo "== $lib"
   SRT_LIB=$PWD/$lib python scripts/variant_time.py 1 2 2>&1 | tail -2

@@ -411,12 +411,19 @@ __device__ __forceinline__ int scan_shapes(const DevScene &sc, vec3 o, vec3 d, v
 
 // Position and shading normal of the winning hit (render.cl:311-312, :337-343, :361-362) followed by
 // the front-face flip (:372-375).
+// (finish_hit_at: the same from a position already computed as origin + direction * t, :311 / :337 / :361)
+__device__ __forceinline__ void finish_hit_at(const DevScene &sc, const Hit &hit, vec3 pos, vec3 d, vec3 &n, bool &front,
+                                              int &material);
 __device__ __forceinline__ void finish_hit(const DevScene &sc, const Hit &hit, vec3 o, vec3 d, vec3 &pos,
                                            vec3 &n, bool &front, int &material) {
+	pos = cfma3(d, hit.t, o);
+	finish_hit_at(sc, hit, pos, d, n, front, material);
+}
+__device__ __forceinline__ void finish_hit_at(const DevScene &sc, const Hit &hit, vec3 pos, vec3 d, vec3 &n, bool &front,
+                                              int &material) {
 	const int4 hdr = __ldg(&sc.shape_hdr[hit.shape]);
 	const float4 a = __ldg(&sc.shape_a[hit.shape]);
 	material = hdr.y;
-	pos = cfma3(d, hit.t, o);
 	if (hdr.x == SHAPE_SPHERE) {
 		vec3 r = pos - xyz(a);
 		n = mk(div_(r.x, a.w), div_(r.y, a.w), div_(r.z, a.w));
@@ -556,7 +563,7 @@ __device__ __forceinline__ void scatter(const DevScene &sc, int material, vec3 p
 #define SRT_MIN_BLOCKS 4
 #endif
 #ifndef SRT_MIN_BLOCKS_ANALYTIC
-#define SRT_MIN_BLOCKS_ANALYTIC 8
+#define SRT_MIN_BLOCKS_ANALYTIC 7
 #endif
 #ifndef SRT_MIN_BLOCKS_BVH
 #define SRT_MIN_BLOCKS_BVH 6
@@ -870,7 +877,14 @@ __device__ __forceinline__ void start_path(const RenderParams &p, unsigned int i
 constexpr int QUEUE_SLOTS = 64;  // < 32 left over + <= 32 pushed per trip
 constexpr int RAYQ_WORDS = 5;    // item, seed, d.xyz          (origin = camera position)
 constexpr int SKYQ_WORDS = 10;   // item, color.xyz, mask.xyz, d.xyz
-constexpr int QUEUE_WARP_BYTES = (RAYQ_WORDS + SKYQ_WORDS) * QUEUE_SLOTS * 4;
+// Wavefront schedule of the queue builds (SRT_WAVEFRONT, render_wavefront): hits go through a third ring, so that hit
+// shading -- 60 % of the instructions of an analytic scene -- always runs with 32 lanes instead of the ~25 whose ray hit
+// something in that trip.
+#ifndef SRT_WAVEFRONT
+#define SRT_WAVEFRONT 1
+#endif
+constexpr int HITQ_WORDS = 16;   // item, seed, position.xyz, d.xyz, mask.xyz, color.xyz, shape << 8 | bounce, triangle
+constexpr int QUEUE_WARP_BYTES = (RAYQ_WORDS + SKYQ_WORDS + (SRT_WAVEFRONT ? HITQ_WORDS : 0)) * QUEUE_SLOTS * 4;
 constexpr int QUEUE_SMEM_BYTES = (SRT_RENDER_THREADS / 32) * QUEUE_WARP_BYTES;
 constexpr int BIG_SKYQ_BYTES = SRT_BIG_SKYQ ? (SRT_RENDER_THREADS / 32) * SKYQ_WORDS * QUEUE_SLOTS * 4 : 0;
 
@@ -882,6 +896,204 @@ constexpr int BIG_SKYQ_BYTES = SRT_BIG_SKYQ ? (SRT_RENDER_THREADS / 32) * SKYQ_W
 // through their hierarchy inside the scan.
 // MODE_ANALYTIC_CONST is MODE_ANALYTIC for scenes of at most CONST_SHAPES shapes, scanning the constant-bank table.
 enum { MODE_ANALYTIC = 0, MODE_SMALL_MODELS = 1, MODE_BIG_MODELS = 2, MODE_BVH = 3, MODE_ANALYTIC_CONST = 4 };
+// ---- wavefront schedule of the queue builds (analytic scenes, small models, BVH) ----------------------------------
+// One trip of a warp:
+//   1. SHADE   if 32 hit records are queued (or the frame is running dry): every lane pops one {item, seed, position,
+//              direction, throughput, radiance, shape, bounce} and runs finish_hit + emission + scatter (render.cl:406-462).
+//              A lane whose path goes on now holds its next ray.
+//   2. REFILL  the other lanes pop fresh camera rays (generated 32 at a time, all lanes, as before).
+//   3. SCAN    closest_intersection for all 32 rays (render.cl:293-378).
+//   4. PUSH    hits into the hit ring, escaped paths into the sky ring (evaluated 32 at a time, render.cl:463-466).
+// Path state lives in registers only WITHIN a trip (ray -> scan -> record; record -> shade -> ray) and in shared memory
+// between scan and shade, so the three expensive stages each run with all 32 lanes: the scan always did, the sky box and
+// the camera rays did through their rings, and hit shading -- the bulk of the instructions -- no longer runs with only
+// the ~25 lanes whose ray happened to hit something in that trip.  Every path executes exactly the operations it
+// executed before, in the same order; only which lane executes them changes.
+template <bool COUNT, int MODE>
+__device__ __forceinline__ void render_wavefront(const RenderParams &p, const DevScene &sc, const ShapeTable &tab,
+                                                 float4 *__restrict__ scratch, unsigned long long *__restrict__ cursor,
+                                                 Counters &cnt, unsigned char *smem_raw) {
+	const unsigned FULL = 0xffffffffu;
+	constexpr bool MODELS = MODE != MODE_ANALYTIC && MODE != MODE_ANALYTIC_CONST;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const unsigned lt_mask = (1u << lane) - 1u;
+	uint32_t *rayq = reinterpret_cast<uint32_t *>(smem_raw + warp * QUEUE_WARP_BYTES);
+	float *skyq = reinterpret_cast<float *>(rayq + RAYQ_WORDS * QUEUE_SLOTS);
+	uint32_t *hitq = reinterpret_cast<uint32_t *>(skyq + SKYQ_WORDS * QUEUE_SLOTS);
+	int ray_head = 0, ray_count = 0, sky_head = 0, sky_count = 0, hit_head = 0, hit_count = 0;  // warp-uniform
+	bool exhausted = false;
+	const vec3 cam_origin = mk(p.c2w[12], p.c2w[13], p.c2w[14]);
+
+	auto flush_sky = [&](int n) {  // mask *= sky, color += mask (:464-465) for n <= 32 queued records, one per lane
+		if (lane < n) {
+			const int sl = (sky_head + lane) & (QUEUE_SLOTS - 1);
+			const unsigned int it = __float_as_uint(skyq[0 * QUEUE_SLOTS + sl]);
+			const vec3 c = mk(skyq[1 * QUEUE_SLOTS + sl], skyq[2 * QUEUE_SLOTS + sl], skyq[3 * QUEUE_SLOTS + sl]);
+			vec3 m = mk(skyq[4 * QUEUE_SLOTS + sl], skyq[5 * QUEUE_SLOTS + sl], skyq[6 * QUEUE_SLOTS + sl]);
+			const vec3 dir = mk(skyq[7 * QUEUE_SLOTS + sl], skyq[8 * QUEUE_SLOTS + sl], skyq[9 * QUEUE_SLOTS + sl]);
+			m = m * sky_box(sc, dir);
+			const vec3 r = c + m;
+			scratch[it] = make_float4(r.x, r.y, r.z, 0.f);
+		}
+		sky_head = (sky_head + n) & (QUEUE_SLOTS - 1);
+		sky_count -= n;
+		__syncwarp();
+	};
+
+	for (;;) {
+		bool has_ray = false;
+		unsigned int item = 0;
+		int bounce = 0;
+		uint32_t seed = 0;
+		vec3 o = mk(0, 0, 0), d = mk(0, 0, 1), mask = mk(1, 1, 1), color = mk(0, 0, 0);
+
+		// -- 1. shade 32 queued hits (fewer only when no fresh ray is left to wait for)
+		const bool dry = exhausted && ray_count == 0;
+		if (hit_count >= 32 || (dry && hit_count > 0)) {
+			const int n = min(hit_count, 32);
+			if (lane < n) {
+				const int sl = (hit_head + lane) & (QUEUE_SLOTS - 1);
+				item = hitq[0 * QUEUE_SLOTS + sl];
+				seed = hitq[1 * QUEUE_SLOTS + sl];
+				const vec3 pos = mk(__uint_as_float(hitq[2 * QUEUE_SLOTS + sl]), __uint_as_float(hitq[3 * QUEUE_SLOTS + sl]),
+				                    __uint_as_float(hitq[4 * QUEUE_SLOTS + sl]));
+				d = mk(__uint_as_float(hitq[5 * QUEUE_SLOTS + sl]), __uint_as_float(hitq[6 * QUEUE_SLOTS + sl]),
+				       __uint_as_float(hitq[7 * QUEUE_SLOTS + sl]));
+				mask = mk(__uint_as_float(hitq[8 * QUEUE_SLOTS + sl]), __uint_as_float(hitq[9 * QUEUE_SLOTS + sl]),
+				          __uint_as_float(hitq[10 * QUEUE_SLOTS + sl]));
+				color = mk(__uint_as_float(hitq[11 * QUEUE_SLOTS + sl]), __uint_as_float(hitq[12 * QUEUE_SLOTS + sl]),
+				           __uint_as_float(hitq[13 * QUEUE_SLOTS + sl]));
+				const uint32_t sb = hitq[14 * QUEUE_SLOTS + sl];
+				Hit hit = {0.f, (int)(sb >> 8), MODELS ? (int)hitq[15 * QUEUE_SLOTS + sl] : -1};
+				bounce = (int)(sb & 255u);
+				if (COUNT) cnt.hits += 1;
+				vec3 n_;
+				bool front;
+				int material;
+				finish_hit_at(sc, hit, pos, d, n_, front, material);
+				bool done;
+				if (p.show_normals) {  // :407-410
+					color = mk(cfma_(n_.x, 0.5f, 0.5f), cfma_(n_.y, 0.5f, 0.5f), cfma_(n_.z, 0.5f, 0.5f));
+					done = true;
+				} else {
+					const float4 m0 = __ldg(&sc.materials[4 * material + 0]);
+					const float4 em = __ldg(&sc.materials[4 * material + 3]);
+					color = color + (mask * xyz(em)) * m0.w;  // :413
+					if (bounce == p.num_bounces - 1) {         // :415-416
+						done = true;
+					} else {
+						const float4 m1 = __ldg(&sc.materials[4 * material + 1]);
+						scatter(sc, material, pos, n_, front, seed, o, d, mask, m0, m1);
+						bounce += 1;
+						done = false;
+					}
+				}
+				if (done) scratch[item] = make_float4(color.x, color.y, color.z, 0.f);  // summed per pixel in sample order later
+				else has_ray = true;
+			}
+			hit_head = (hit_head + n) & (QUEUE_SLOTS - 1);
+			hit_count -= n;
+			__syncwarp();
+		}
+
+		// -- 2. the other lanes take fresh camera rays (start_path, 32 at a time with every lane active)
+		const unsigned need = __ballot_sync(FULL, !has_ray);
+		if (need) {
+			const int want = __popc(need);
+			if (ray_count < want && !exhausted) {
+				unsigned int base = 0;
+				if (lane == 0) {  // 64-bit cursor: stepping past the end can never wrap into the item range
+					const unsigned long long b = atomicAdd(cursor, 32ull);
+					base = b < (unsigned long long)p.total_items ? (unsigned int)b : 0xffffffffu;
+				}
+				base = __shfl_sync(FULL, base, 0);
+				const unsigned int it = base + lane;
+				const bool valid = base != 0xffffffffu && it < p.total_items;
+				const unsigned vm = __ballot_sync(FULL, valid);
+				if (valid) {
+					uint32_t sd;
+					vec3 oo, dd;
+					start_path(p, it, sd, oo, dd);
+					const int sl = (ray_head + ray_count + __popc(vm & lt_mask)) & (QUEUE_SLOTS - 1);
+					rayq[0 * QUEUE_SLOTS + sl] = it;
+					rayq[1 * QUEUE_SLOTS + sl] = sd;
+					rayq[2 * QUEUE_SLOTS + sl] = __float_as_uint(dd.x);
+					rayq[3 * QUEUE_SLOTS + sl] = __float_as_uint(dd.y);
+					rayq[4 * QUEUE_SLOTS + sl] = __float_as_uint(dd.z);
+					if (COUNT) cnt.samples += 1;
+				}
+				ray_count += __popc(vm);
+				exhausted = vm != FULL;
+				__syncwarp();
+			}
+			if (!has_ray) {
+				const int r = __popc(need & lt_mask);
+				if (r < ray_count) {
+					const int sl = (ray_head + r) & (QUEUE_SLOTS - 1);
+					item = rayq[0 * QUEUE_SLOTS + sl];
+					seed = rayq[1 * QUEUE_SLOTS + sl];
+					d = mk(__uint_as_float(rayq[2 * QUEUE_SLOTS + sl]), __uint_as_float(rayq[3 * QUEUE_SLOTS + sl]),
+					       __uint_as_float(rayq[4 * QUEUE_SLOTS + sl]));
+					o = cam_origin;
+					mask = mk(1, 1, 1);
+					color = mk(0, 0, 0);
+					bounce = 0;
+					has_ray = true;
+				}
+			}
+			const int popped = min(want, ray_count);
+			ray_head = (ray_head + popped) & (QUEUE_SLOTS - 1);
+			ray_count -= popped;
+			__syncwarp();
+		}
+		if (!__any_sync(FULL, has_ray)) {
+			if (hit_count == 0) break;  // nothing in flight: the frame is done for this warp
+			continue;                   // only queued hits are left: the next trip shades them
+		}
+
+		// -- 3. closest_intersection for every ray of the trip, :293-378
+		Hit hit = {__int_as_float(0x7f800000), -1, -1};
+		if (has_ray) {
+			if (COUNT) cnt.bounces += 1;
+			const vec3 inv = MODELS ? mk(rcp_(d.x), rcp_(d.y), rcp_(d.z)) : mk(0, 0, 0);
+			scan_shapes<COUNT, false, MODELS, MODE == MODE_BVH, MODE == MODE_ANALYTIC_CONST>(sc, o, d, inv, 0, hit, cnt, &tab);
+		}
+
+		// -- 4. hits -> hit ring (position = origin + direction * t, :311 / :337 / :361); escaped paths -> sky ring
+		const bool is_hit = has_ray && hit.shape >= 0, is_miss = has_ray && hit.shape < 0;
+		const unsigned hm = __ballot_sync(FULL, is_hit), sm = __ballot_sync(FULL, is_miss);
+		if (is_hit) {
+			const vec3 pos = cfma3(d, hit.t, o);
+			const int sl = (hit_head + hit_count + __popc(hm & lt_mask)) & (QUEUE_SLOTS - 1);
+			hitq[0 * QUEUE_SLOTS + sl] = item;
+			hitq[1 * QUEUE_SLOTS + sl] = seed;
+			hitq[2 * QUEUE_SLOTS + sl] = __float_as_uint(pos.x), hitq[3 * QUEUE_SLOTS + sl] = __float_as_uint(pos.y);
+			hitq[4 * QUEUE_SLOTS + sl] = __float_as_uint(pos.z);
+			hitq[5 * QUEUE_SLOTS + sl] = __float_as_uint(d.x), hitq[6 * QUEUE_SLOTS + sl] = __float_as_uint(d.y);
+			hitq[7 * QUEUE_SLOTS + sl] = __float_as_uint(d.z);
+			hitq[8 * QUEUE_SLOTS + sl] = __float_as_uint(mask.x), hitq[9 * QUEUE_SLOTS + sl] = __float_as_uint(mask.y);
+			hitq[10 * QUEUE_SLOTS + sl] = __float_as_uint(mask.z);
+			hitq[11 * QUEUE_SLOTS + sl] = __float_as_uint(color.x), hitq[12 * QUEUE_SLOTS + sl] = __float_as_uint(color.y);
+			hitq[13 * QUEUE_SLOTS + sl] = __float_as_uint(color.z);
+			hitq[14 * QUEUE_SLOTS + sl] = ((uint32_t)hit.shape << 8) | (uint32_t)bounce;
+			if (MODELS) hitq[15 * QUEUE_SLOTS + sl] = (uint32_t)hit.tri;
+		}
+		if (is_miss) {
+			if (COUNT) cnt.sky += 1;
+			const int sl = (sky_head + sky_count + __popc(sm & lt_mask)) & (QUEUE_SLOTS - 1);
+			skyq[0 * QUEUE_SLOTS + sl] = __uint_as_float(item);
+			skyq[1 * QUEUE_SLOTS + sl] = color.x, skyq[2 * QUEUE_SLOTS + sl] = color.y, skyq[3 * QUEUE_SLOTS + sl] = color.z;
+			skyq[4 * QUEUE_SLOTS + sl] = mask.x, skyq[5 * QUEUE_SLOTS + sl] = mask.y, skyq[6 * QUEUE_SLOTS + sl] = mask.z;
+			skyq[7 * QUEUE_SLOTS + sl] = d.x, skyq[8 * QUEUE_SLOTS + sl] = d.y, skyq[9 * QUEUE_SLOTS + sl] = d.z;
+		}
+		hit_count += __popc(hm);
+		sky_count += __popc(sm);
+		__syncwarp();
+		if (sky_count >= 32) flush_sky(32);
+	}
+	if (sky_count > 0) flush_sky(sky_count);
+}
+
 template <bool COUNT, int MODE>
 __global__ void __launch_bounds__(RENDER_THREADS, MODE == MODE_BIG_MODELS ? SRT_MIN_BLOCKS : (MODE == MODE_BVH ? SRT_MIN_BLOCKS_BVH : SRT_MIN_BLOCKS_ANALYTIC))
 render_kernel(const __grid_constant__ RenderParams p, const __grid_constant__ DevScene sc,
@@ -897,6 +1109,18 @@ render_kernel(const __grid_constant__ RenderParams p, const __grid_constant__ De
 
 	// per-warp ring of triangle tiles + one mbarrier per stage
 	extern __shared__ __align__(128) unsigned char smem_raw[];
+	if (QUEUES && SRT_WAVEFRONT) {  // the queue builds run the wavefront schedule (the loop below is then the dense-sweep build's)
+		render_wavefront<COUNT, MODE>(p, sc, tab, scratch, cursor, cnt, smem_raw);
+		if (COUNT) {
+			unsigned long long *c = reinterpret_cast<unsigned long long *>(&cnt);
+			for (int k = 0; k < 6; ++k) {
+				unsigned long long v = c[k];
+				for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(FULL, v, off);
+				if (lane == 0 && v) atomicAdd(reinterpret_cast<unsigned long long *>(counters) + k, v);
+			}
+		}
+		return;
+	}
 	const int warp = threadIdx.x >> 5;
 	unsigned char *wsmem = smem_raw + warp * WARP_SMEM_BYTES;
 	const uint32_t wsmem_s = smem_u32(wsmem);

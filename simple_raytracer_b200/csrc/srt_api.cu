@@ -241,6 +241,11 @@ int launch_render_impl(srt_tracer *t, const srt::RenderParams &p) {
 
 template <bool COUNT>
 int launch_params(srt_tracer *t, const srt::RenderParams &p) {
+	// the wavefront builds pack (shape << 8 | bounce) into one word of a hit record: launches outside that range run
+	// on the general machine (MODE_BIG_MODELS handles every scene -- small models are intersected inline there too --
+	// with the reference's brute-force triangle loop, whatever srt_set_accel says)
+	if (SRT_WAVEFRONT && (p.num_bounces > 256 || t->n_shapes >= ((size_t)1 << 24)))
+		return launch_render_impl<COUNT, srt::MODE_BIG_MODELS>(t, p);
 	if (!t->has_models && t->n_shapes <= (size_t)srt::CONST_SHAPES) return launch_render_impl<COUNT, srt::MODE_ANALYTIC_CONST>(t, p);
 	if (!t->has_models) return launch_render_impl<COUNT, srt::MODE_ANALYTIC>(t, p);
 	if (t->accel == SRT_ACCEL_BVH && t->bvh_ready && t->has_big_models) return launch_render_impl<COUNT, srt::MODE_BVH>(t, p);
