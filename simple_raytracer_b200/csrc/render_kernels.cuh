@@ -537,10 +537,11 @@ __device__ __forceinline__ void scatter(const DevScene &sc, int material, vec3 p
 		float ki = 2.0f * dot(rough, n);                        // in_dir = reflect(rough, n), :440
 		vec3 in_dir = mk(cfma_(-ki, n.x, rough.x), cfma_(-ki, n.y, rough.y), cfma_(-ki, n.z, rough.z));
 		float mu = front ? rcp_(m1.y) : m1.y;             // :442
+		const float r0 = front ? m1.z : m1.w;             // shlick's r0 for this mu, precomputed per material (:174-175)
 		float cos_theta = min_(1.0f, dot(in_dir, -n));          // :443
 		float sin_theta = sqrt_(cfma_(-cos_theta, cos_theta, 1.0f));
 		bool reflected_t = mu * sin_theta > 1.0f;               // :446
-		if (!reflected_t) reflected_t = schlick_(mu, cos_theta) > random_float(seed);  // :447 (short-circuit)
+		if (!reflected_t) reflected_t = schlick_from_r0(r0, cos_theta) > random_float(seed);  // :447 (short-circuit)
 		if (reflected_t) {
 			nd = rough;                                         // :450
 		} else {
@@ -1514,6 +1515,20 @@ prepare_triangles_kernel(const float4 *__restrict__ aos /* 6 float4 per triangle
 	q[4] = make_float4(0.f, 0.f, 0.f, 0.f);
 	const float k = n1v0 + 3.0f * emax;  // non-negative (or NaN, which the filter then passes): orders like its bits
 	atomicMax(reinterpret_cast<unsigned int *>(model_k + sp.shape), __float_as_uint(k == k ? k : __int_as_float(0x7f800000)));
+}
+
+// ---- scene upload: per-material constants --------------------------------------------------------------------------
+// The device copy of a Material record keeps the reference's 64 bytes; its two padding floats (bytes 24..31, unused by
+// render.cl:17-27) receive shlick_reflectance's r0 = ((1 - mu) / (1 + mu))^2 (:174-175, FP64 division) for the two
+// values mu can take at that material -- 1 / refraction_index entering (:442), refraction_index leaving -- computed by
+// the same device function the per-hit code used to call, so that no hit pays for a double-precision division.
+__global__ void prepare_materials_kernel(float4 *__restrict__ materials, int n) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	float4 m1 = materials[4 * i + 1];
+	m1.z = schlick_r0(rcp_(m1.y));
+	m1.w = schlick_r0(m1.y);
+	materials[4 * i + 1] = m1;
 }
 
 // ---- device math self-test -------------------------------------------------------------------

@@ -461,8 +461,11 @@ int srt_upload_scene(srt_tracer *t, const srt_shape *shapes, size_t n_shapes, co
 		SRT_CUDA(t, cudaMemcpyAsync(t->shape_b.ptr, b.data(), n_shapes * sizeof(float4), cudaMemcpyHostToDevice, st));
 		SRT_CUDA(t, cudaMemcpyAsync(t->model_xf.ptr, xf.data(), 4 * n_shapes * sizeof(float4), cudaMemcpyHostToDevice, st));
 	}
-	if (n_materials)
+	if (n_materials) {
 		SRT_CUDA(t, cudaMemcpyAsync(t->materials.ptr, materials, n_materials * sizeof(srt_material), cudaMemcpyHostToDevice, st));
+		srt::prepare_materials_kernel<<<((int)n_materials + 127) / 128, 128, 0, st>>>(t->materials.ptr, (int)n_materials);
+		SRT_CUDA(t, cudaGetLastError());
+	}
 	if (n_triangles)
 		SRT_CUDA(t, cudaMemcpyAsync(t->tri_aos.ptr, triangles, n_triangles * sizeof(srt_triangle), cudaMemcpyHostToDevice, st));
 	if (!spans.empty()) {
