@@ -166,6 +166,12 @@ int srt_set_accel(srt_tracer *t, int accel);
  * (u range) above; the other two force one kind for every model (parity tests run both, tuning). */
 enum { SRT_FILTER_AUTO = 0, SRT_FILTER_ONE_STRIP = 1, SRT_FILTER_TWO_STRIP = 2 };
 int srt_set_sweep_filter(srt_tracer *t, int mode);
+/* How scenes without large models schedule a warp's work (results are bit-identical either way): PLAIN shades a hit in
+ * the lane and trip that found it, WAVEFRONT passes hits through a per-warp ring and shades them 32 at a time (faster
+ * on long launches, slower on launches of a few items per thread); AUTO picks by launch size.  WAVEFRONT is honoured
+ * when the launch fits its records (at most 256 bounces, fewer than 2^24 shapes).  Parity tests run both; tuning. */
+enum { SRT_SCHEDULE_AUTO = 0, SRT_SCHEDULE_PLAIN = 1, SRT_SCHEDULE_WAVEFRONT = 2 };
+int srt_set_schedule(srt_tracer *t, int schedule);
 int srt_read_canvas(srt_tracer *t, float *rgba_out);               /* width*height*4 floats; synchronises */
 int srt_write_canvas(srt_tracer *t, const float *rgba_in);         /* restore an accumulation (checkpoint/resume) */
 int srt_canvas_device_ptr(srt_tracer *t, void **ptr, size_t *bytes); /* for NCCL reduce of per-GPU canvases */

@@ -1095,7 +1095,11 @@ __device__ __forceinline__ void render_wavefront(const RenderParams &p, const De
 	if (sky_count > 0) flush_sky(sky_count);
 }
 
-template <bool COUNT, int MODE>
+// WF: the queue builds exist with both schedules -- wavefront (hits shaded 32 at a time through the hit ring) for
+// launches that keep every thread busy for many items, plain (hits shaded in place) for short ones, where queueing a
+// hit until 32 are there only lengthens the ragged end (BASELINE config 1, 3 items per thread: +6 % plain) and for
+// launches whose bounce count does not fit the hit record's 8 bits.
+template <bool COUNT, int MODE, bool WF>
 __global__ void __launch_bounds__(RENDER_THREADS, MODE == MODE_BIG_MODELS ? SRT_MIN_BLOCKS : (MODE == MODE_BVH ? SRT_MIN_BLOCKS_BVH : SRT_MIN_BLOCKS_ANALYTIC))
 render_kernel(const __grid_constant__ RenderParams p, const __grid_constant__ DevScene sc,
               const __grid_constant__ ShapeTable tab, float4 *__restrict__ scratch,
@@ -1110,7 +1114,7 @@ render_kernel(const __grid_constant__ RenderParams p, const __grid_constant__ De
 
 	// per-warp ring of triangle tiles + one mbarrier per stage
 	extern __shared__ __align__(128) unsigned char smem_raw[];
-	if (QUEUES && SRT_WAVEFRONT) {  // the queue builds run the wavefront schedule (the loop below is then the dense-sweep build's)
+	if (QUEUES && WF) {  // the wavefront schedule (the loop below is the plain schedule and the dense-sweep build)
 		render_wavefront<COUNT, MODE>(p, sc, tab, scratch, cursor, cnt, smem_raw);
 		if (COUNT) {
 			unsigned long long *c = reinterpret_cast<unsigned long long *>(&cnt);

@@ -97,7 +97,8 @@ struct srt_tracer {
 
 	int band_h = 1, band_i = 0, band_n = 1;
 	int uv_max_tris = srt::UV_MAX_TRIS;  // srt_set_sweep_filter
-	int render_grid[2][5] = {{0, 0, 0, 0, 0}, {0, 0, 0, 0, 0}};  // [counted][mode]
+	int schedule = SRT_SCHEDULE_AUTO;    // srt_set_schedule
+	int render_grid[2][5][2] = {};  // [counted][mode][wavefront]
 	srt::ShapeTable shape_table{};  // the first CONST_SHAPES shape records, passed as a kernel parameter
 
 	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing;  // kernel launches since last query
@@ -198,11 +199,26 @@ int make_params(srt_tracer *t, const srt_render_data *rd, srt::RenderParams &p) 
 	return SRT_OK;
 }
 
+template <bool COUNT, int MODE, bool WF>
+int launch_render_impl(srt_tracer *t, const srt::RenderParams &p);
+
+// The wavefront schedule queues a hit until 32 are there to shade: worth it once a launch keeps every thread busy for
+// many items (+1.6 % on BASELINE config 2), not for a launch of a few items per thread (config 1: -6 %).  Its hit record
+// keeps the bounce count in 8 bits and the shape index in 24; anything else runs the plain schedule.
 template <bool COUNT, int MODE>
 int launch_render_impl(srt_tracer *t, const srt::RenderParams &p) {
-	auto kernel = srt::render_kernel<COUNT, MODE>;
+	const bool fits = p.num_bounces <= 256 && t->n_shapes < ((size_t)1 << 24);
+	const bool wf = SRT_WAVEFRONT && MODE != srt::MODE_BIG_MODELS && fits && t->schedule != SRT_SCHEDULE_PLAIN &&
+	                (p.total_items >= (4u << 20) || t->schedule == SRT_SCHEDULE_WAVEFRONT);
+	if (MODE != srt::MODE_BIG_MODELS && wf) return launch_render_impl<COUNT, MODE, MODE != srt::MODE_BIG_MODELS>(t, p);
+	return launch_render_impl<COUNT, MODE, false>(t, p);
+}
+
+template <bool COUNT, int MODE, bool WF>
+int launch_render_impl(srt_tracer *t, const srt::RenderParams &p) {
+	auto kernel = srt::render_kernel<COUNT, MODE, WF>;
 	const int smem = MODE == srt::MODE_BIG_MODELS ? srt::RENDER_SMEM_BYTES + srt::BIG_SKYQ_BYTES : srt::QUEUE_SMEM_BYTES;
-	int &grid = t->render_grid[COUNT ? 1 : 0][MODE];
+	int &grid = t->render_grid[COUNT ? 1 : 0][MODE][WF ? 1 : 0];
 	if (grid == 0) {
 		int per_sm = 0;
 		if (smem) SRT_CUDA(t, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -241,11 +257,6 @@ int launch_render_impl(srt_tracer *t, const srt::RenderParams &p) {
 
 template <bool COUNT>
 int launch_params(srt_tracer *t, const srt::RenderParams &p) {
-	// the wavefront builds pack (shape << 8 | bounce) into one word of a hit record: launches outside that range run
-	// on the general machine (MODE_BIG_MODELS handles every scene -- small models are intersected inline there too --
-	// with the reference's brute-force triangle loop, whatever srt_set_accel says)
-	if (SRT_WAVEFRONT && (p.num_bounces > 256 || t->n_shapes >= ((size_t)1 << 24)))
-		return launch_render_impl<COUNT, srt::MODE_BIG_MODELS>(t, p);
 	if (!t->has_models && t->n_shapes <= (size_t)srt::CONST_SHAPES) return launch_render_impl<COUNT, srt::MODE_ANALYTIC_CONST>(t, p);
 	if (!t->has_models) return launch_render_impl<COUNT, srt::MODE_ANALYTIC>(t, p);
 	if (t->accel == SRT_ACCEL_BVH && t->bvh_ready && t->has_big_models) return launch_render_impl<COUNT, srt::MODE_BVH>(t, p);
@@ -672,6 +683,14 @@ int srt_set_row_bands(srt_tracer *t, int band_height, int band_index, int band_c
 	}
 	if (band_height < 1 || band_index < 0 || band_index >= band_count) return fail(t, SRT_ERR_INVALID, "bad row bands");
 	t->band_h = band_height, t->band_i = band_index, t->band_n = band_count;
+	return SRT_OK;
+}
+
+int srt_set_schedule(srt_tracer *t, int schedule) {
+	if (!t) return SRT_ERR_INVALID;
+	if (schedule != SRT_SCHEDULE_AUTO && schedule != SRT_SCHEDULE_PLAIN && schedule != SRT_SCHEDULE_WAVEFRONT)
+		return fail(t, SRT_ERR_INVALID, "unknown schedule %d", schedule);
+	t->schedule = schedule;
 	return SRT_OK;
 }
 

@@ -51,6 +51,7 @@ def load_library():
         "srt_set_row_bands": [vp, i32, i32, i32],
         "srt_set_accel": [vp, i32],
         "srt_set_sweep_filter": [vp, i32],
+        "srt_set_schedule": [vp, i32],
         "srt_read_canvas": [vp, vp],
         "srt_write_canvas": [vp, vp],
         "srt_canvas_device_ptr": [vp, pp, ctypes.POINTER(sz)],
@@ -119,6 +120,8 @@ class Tracer:
         self.scene_data = np.zeros(1, SCENE_DATA)
         if os.environ.get("SRT_SWEEP_FILTER"):  # test / tuning hook: "auto", "one", "two" (bit-identical results)
             self.set_sweep_filter(os.environ["SRT_SWEEP_FILTER"])
+        if os.environ.get("SRT_SCHEDULE"):  # test / tuning hook: "auto", "plain", "wavefront" (bit-identical results)
+            self.set_schedule(os.environ["SRT_SCHEDULE"])
 
     # -- reference surface ----------------------------------------------------------------------
     def update_scene(self, shapes, triangles, materials):
@@ -200,6 +203,10 @@ class Tracer:
         """srt_set_accel: "none" (default: the reference's brute-force triangle loop, bit-exact) or "bvh" (labelled
         extension outside the parity path)."""
         self._check(self._lib.srt_set_accel(self._h, {"none": 0, "bvh": 1}[accel]))
+
+    def set_schedule(self, schedule):
+        """srt_set_schedule: "auto" | "plain" | "wavefront" -- how scenes without large models schedule a warp's work."""
+        self._check(self._lib.srt_set_schedule(self._h, {"auto": 0, "plain": 1, "wavefront": 2}[schedule]))
 
     def set_sweep_filter(self, mode):
         """srt_set_sweep_filter: "auto" | "one" | "two" -- which conservative filter precedes the exact triangle test."""

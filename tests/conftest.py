@@ -48,3 +48,12 @@ def assert_bit_equal(a, b, what=""):
         i = np.argwhere(neq)[0]
         raise AssertionError(f"{what}: {n} of {a.size} values differ; first at {tuple(i)}: "
                              f"{a[tuple(i)]!r} vs {b[tuple(i)]!r}")
+
+
+@pytest.fixture(params=["plain", "wavefront"])
+def schedule(request, monkeypatch):
+    """Run a parity test under BOTH warp schedules of the analytic / small-model kernel builds (srt_set_schedule through
+    the Tracer's SRT_SCHEDULE hook): the automatic choice would give every small test launch the plain schedule and
+    only full-size launches the wavefront one."""
+    monkeypatch.setenv("SRT_SCHEDULE", request.param)
+    return request.param

@@ -36,7 +36,7 @@ def test_primary_hit_ids_and_t_bit_exact(ctx, cfg, w, h, ns, launches):
 
 
 @pytest.mark.parametrize("cfg,w,h,ns,launches", CASES)
-def test_canvas_bit_exact_and_counters(ctx, cfg, w, h, ns, launches):
+def test_canvas_bit_exact_and_counters(ctx, cfg, w, h, ns, launches, schedule):
     sc = scenes.CONFIGS[cfg](w, h)
     oc, ocnt = oracle_canvas(ctx["oracle"], sc, ctx["sky"], launches, num_samples=ns)
     tr = make_tracer(sc, ctx["sky"])
@@ -57,7 +57,7 @@ needs_ref = pytest.mark.skipif(not __import__("oracle").ref_available(), reason=
 
 @needs_ref
 @pytest.mark.parametrize("cfg,w,h,ns,launches", CASES)
-def test_canvas_bit_exact_against_the_reference_kernel(ctx, cfg, w, h, ns, launches):
+def test_canvas_bit_exact_against_the_reference_kernel(ctx, cfg, w, h, ns, launches, schedule):
     """The CUDA path against /root/reference/src/render.cl itself (oracle/_ref, built by g++): canvases and
     resolved images bit-identical, primary-hit shape ids identical on every pixel."""
     oracle = ctx["oracle"]
@@ -77,7 +77,7 @@ def test_canvas_bit_exact_against_the_reference_kernel(ctx, cfg, w, h, ns, launc
 
 @needs_ref
 @pytest.mark.parametrize("seed", range(6))
-def test_random_scenes_against_the_reference_kernel(ctx, seed):
+def test_random_scenes_against_the_reference_kernel(ctx, seed, schedule):
     oracle = ctx["oracle"]
     sc = random_scene(seed, width=160, height=96, mesh_tris=(0, 20, 200)[seed % 3])
     tr = make_tracer(sc, ctx["sky"])
@@ -90,7 +90,7 @@ def test_random_scenes_against_the_reference_kernel(ctx, seed):
 
 
 @pytest.mark.parametrize("cfg", [1, 3])
-def test_show_normals_image(ctx, cfg):
+def test_show_normals_image(ctx, cfg, schedule):
     sc = scenes.CONFIGS[cfg](160, 120)
     rd = sc.render_data(0, show_normals=True, num_samples=1)
     oc, _ = ctx["oracle"].render(rd, sc.scene_data, sc.shapes, sc.triangles, sc.materials, ctx["sky"])
@@ -147,7 +147,7 @@ def test_golden_fixture(cfg):
 
 
 @needs_ref
-def test_random_launch_parameters_against_the_reference_kernel(ctx, small_sky):
+def test_random_launch_parameters_against_the_reference_kernel(ctx, small_sky, schedule):
     """Launch parameters themselves randomised: image size (down to 1x1), sample / bounce counts (0 bounces too), time
     seeds (0, wrapping products), camera pose, fov, show_normals -- each against render.cl, single launches and a batch."""
     oracle = ctx["oracle"]
