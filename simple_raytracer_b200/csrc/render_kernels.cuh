@@ -101,6 +101,29 @@ struct RenderParams {
 	int uv_max_tris;           // models of at most this many triangles are swept with the two-strip filter
 };
 
+// Fused frame (srt_render_frame, FUSE builds of render_kernel): everything the reference's Tracer::render does after
+// the `render` launch -- `canvas[id] += color` (render.cl:520-522), kernel `average` (:525-535) and the blocking
+// read of the ARGB8 image (src/tracer.cpp:110-115) -- happens WHILE the frame is still being traced.  The lane that
+// finishes the last sample of a pixel (a per-pixel counter) queues the pixel; the warp resolves 32 queued pixels at a
+// time: samples summed in sample order from scratch (still in L2), canvas updated, ARGB8 written.  Finished rows are
+// counted per band of rows, and the lane that completes a band publishes it in host-mapped memory; the host thread
+// inside srt_render_frame polls those flags and starts the band's device-to-host copy on a second stream at once, so
+// that when the kernel ends only the last band's copy is outstanding (a 1080p frame: 0.16 ms of read-back hidden).
+// The additions are the ones accumulate_kernel + average_kernel perform, in the same order: bit-identical images.
+constexpr int FRAME_MAX_BANDS = 64;
+struct FrameOut {
+	float4 *canvas;
+	uchar4 *output;
+	unsigned int *pix_done;   // per pixel: samples finished in this launch (reset to 0 by the lane that completes it)
+	unsigned int *row_done;   // per row: pixels resolved (reset likewise)
+	unsigned int *band_done;  // per band: rows resolved (reset likewise)
+	volatile unsigned int *host_flags;  // host-mapped, per band: frame epoch of the last completed frame
+	unsigned int epoch;
+	unsigned int num_steps;   // kernel `average`'s argument (ticks_stopped, src/tracer.cpp:111)
+	int band_rows;            // rows per band
+	int ns_shift;             // log2(num_samples) when that is a power of two, else -1
+};
+
 struct Counters {
 	unsigned long long samples, bounces, tri_tests, aabb_pass, hits, sky;
 };
@@ -511,13 +534,27 @@ __device__ __forceinline__ void camera_ray(const RenderParams &p, int gx, int gy
 }
 
 // Scatter at a hit, render.cl:418-462.  Updates o, d, mask; consumes 9 or 10 random numbers.
+// ROLLED: the three normal draws as a rolled loop (one copy of the code instead of three)
+template <bool ROLLED = false>
 __device__ __forceinline__ void scatter(const DevScene &sc, int material, vec3 pos, vec3 n, bool front,
                                         uint32_t &seed, vec3 &o, vec3 &d, vec3 &mask, float4 m0, float4 m1) {
 	o = pos;
 	// random_direction_hemisphere, :156-163
-	float gx = random_float_normal(seed);
-	float gy = random_float_normal(seed);
-	float gz = random_float_normal(seed);
+	float gx = 0.f, gy = 0.f, gz = 0.f;
+	if (ROLLED) {
+		// three draws, ONE copy of the code: in the fused-frame builds the kernel's hot instructions (this loop plus the
+		// in-kernel resolve) would otherwise outgrow the 32 KB L1.5 instruction cache (stalled_no_instruction 0.6 -> 2.2
+		// per issue); the plain builds fit and keep the three inlined copies (1 % faster there)
+#pragma unroll 1
+		for (int k = 0; k < 3; ++k) {
+			gx = gy, gy = gz;
+			gz = random_float_normal(seed);
+		}
+	} else {
+		gx = random_float_normal(seed);
+		gy = random_float_normal(seed);
+		gz = random_float_normal(seed);
+	}
 	vec3 rd = normalize(mk(gx, gy, gz));
 	rd = rd * sign_(dot(n, rd));
 	vec3 random_dir = normalize(n + rd);                       // :421
@@ -851,6 +888,119 @@ __device__ SRT_PHASE_ATTR void triangle_phase(const DevScene &sc, int n, int tri
 	__syncwarp();
 }
 
+// ---- the per-pixel part of kernel `average`, render.cl:525-535 (aces :473-481) -----------------
+__device__ __forceinline__ float aces_sqrt(float x) {
+	const float a = 2.51f, b = 0.03f, c = 2.43f, dd = 0.59f, e = 0.14f;
+	float num = x * cfma_(x, a, b);
+	float den = cfma_(x, cfma_(x, c, dd), e);
+	float r = div_(num, den);
+	r = r > 0.0f ? r : 0.0f;  // clamp; NaN -> 0
+	r = r < 1.0f ? r : 1.0f;
+	return sqrt_(r);
+}
+__device__ __forceinline__ uchar4 argb_pixel(float4 c, float steps) {
+	float r = aces_sqrt(div_(c.x, steps)) * 255.0f;
+	float g = aces_sqrt(div_(c.y, steps)) * 255.0f;
+	float b = aces_sqrt(div_(c.z, steps)) * 255.0f;
+	// uchar4(255, r, g, b): A,R,G,B byte order, float -> uchar by truncation
+	return make_uchar4(255, (unsigned char)(int)r, (unsigned char)(int)g, (unsigned char)(int)b);
+}
+// the same with ONE copy of the per-channel code (a rolled loop that rotates the channels through): for the fused frame,
+// where this sits inside the render kernel and instruction-cache footprint matters more than a few loop instructions
+__device__ __forceinline__ uchar4 argb_pixel_rolled(float4 c, float steps) {
+	float r = c.x, g = c.y, b = c.z;
+#pragma unroll 1
+	for (int k = 0; k < 3; ++k) {
+		const float v = aces_sqrt(div_(r, steps)) * 255.0f;
+		r = g, g = b, b = v;
+	}
+	return make_uchar4(255, (unsigned char)(int)r, (unsigned char)(int)g, (unsigned char)(int)b);
+}
+
+// ---- fused frame: per-warp ring of completed pixels (FrameOut) -----------------------------------------------------
+__device__ __forceinline__ void fence_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+constexpr int PIXQ_SLOTS = 64;  // < 32 left over + <= 32 pushed at a time
+constexpr int PIXQ_BYTES = PIXQ_SLOTS * 4;
+struct PixRing {
+	uint32_t *q;
+	int head, count;  // warp-uniform
+};
+// Resolve n <= 32 queued pixels, one per lane: color = sum of the pixel's samples in sample order (render.cl:494-519),
+// color /= num_samples (:520), canvas[id] += color (:522) -- accumulate_kernel's arithmetic -- then kernel `average`
+// for that pixel; count the pixel towards its row, the row towards its band, and publish a completed band to the host.
+__device__ __noinline__ void flush_pixels(const RenderParams &p, const FrameOut &fo, const float4 *scratch, PixRing &ring,
+                                             int n, int lane) {
+	fence_gpu();  // the samples below were written by other threads (published through pix_done)
+	int row = -1;
+	if (lane < n) {
+		const unsigned int pix = ring.q[(ring.head + lane) & (PIXQ_SLOTS - 1)];  // full frame: local pixel == pixel id
+		float4 c = __ldcg(&fo.canvas[pix]);
+		const float4 *s = scratch + (size_t)pix * p.num_samples;
+		vec3 color = mk(0, 0, 0);
+		for (int k = 0; k < p.num_samples; ++k) color = color + xyz(__ldcg(&s[k]));
+		if (p.inv_ns != 0.0f) {  // x / 2^k == x * 2^-k exactly
+			c.x += color.x * p.inv_ns, c.y += color.y * p.inv_ns, c.z += color.z * p.inv_ns;
+		} else {
+			const float ns_f = (float)p.num_samples;
+			c.x += div_(color.x, ns_f), c.y += div_(color.y, ns_f), c.z += div_(color.z, ns_f);
+		}
+		fo.canvas[pix] = c;
+		fo.output[pix] = argb_pixel_rolled(c, (float)fo.num_steps);
+		row = (int)(pix / (unsigned)p.width);
+		fence_gpu();  // my pixel before the row counter
+	}
+	ring.head = (ring.head + n) & (PIXQ_SLOTS - 1);
+	ring.count -= n;
+	__syncwarp();
+	if (lane < n) {
+		const unsigned act = n >= 32 ? 0xffffffffu : (1u << n) - 1u;
+		const unsigned same = __match_any_sync(act, row);
+		if (lane == __ffs(same) - 1) {  // one atomic per row per flush
+			const unsigned int k = (unsigned)__popc(same);
+			if (atomicAdd(&fo.row_done[row], k) + k == (unsigned)p.width) {
+				fo.row_done[row] = 0;
+				const int band = row / fo.band_rows;
+				const int rows_in_band = min(fo.band_rows, p.height - band * fo.band_rows);
+				fence_gpu();
+				if (atomicAdd(&fo.band_done[band], 1u) + 1u == (unsigned)rows_in_band) {
+					fo.band_done[band] = 0;
+					__threadfence_system();  // the band's ARGB8 pixels before the flag the host (and then a copy engine) acts on
+					fo.host_flags[band] = fo.epoch;
+				}
+			}
+		}
+	}
+	__syncwarp();
+}
+// Every lane of the warp calls this once per site where samples can finish; `fin`: my sample `item` just finished and
+// its radiance is in scratch[item].
+template <bool FUSE>
+__device__ __forceinline__ void sample_done(const RenderParams &p, const FrameOut &fo, const float4 *scratch, PixRing &ring,
+                                            bool fin, unsigned int item, int lane) {
+	if (!FUSE) return;
+	unsigned int lp = 0;
+	bool complete = false;
+	if (fin) {
+		lp = fo.ns_shift >= 0 ? item >> fo.ns_shift : item / (unsigned)p.num_samples;
+		if (p.num_samples == 1) {
+			complete = true;
+		} else {
+			// my sample before the counter: a RELEASE increment (one MEMBAR, and -- unlike a fence -- no L1 invalidation)
+			unsigned int old;
+			asm volatile("atom.add.release.gpu.global.u32 %0, [%1], 1;" : "=r"(old) : "l"(fo.pix_done + lp) : "memory");
+			complete = old == (unsigned)p.num_samples - 1u;
+			if (complete) fo.pix_done[lp] = 0;  // nobody touches this pixel again before the next launch
+		}
+	}
+	const unsigned cm = __ballot_sync(0xffffffffu, complete);
+	if (cm) {
+		if (complete) ring.q[(ring.head + ring.count + __popc(cm & ((1u << lane) - 1u))) & (PIXQ_SLOTS - 1)] = lp;
+		ring.count += __popc(cm);
+		__syncwarp();
+		if (ring.count >= 32) flush_pixels(p, fo, scratch, ring, 32, lane);
+	}
+}
+
 // Start the camera path of work item `item` = local_pixel * num_samples + sample (render.cl:488-516).
 __device__ __forceinline__ void start_path(const RenderParams &p, unsigned int item, uint32_t &seed, vec3 &o, vec3 &d) {
 	const unsigned int launch = p.num_launches > 1 ? item / p.items_per_launch : 0u;
@@ -910,10 +1060,11 @@ enum { MODE_ANALYTIC = 0, MODE_SMALL_MODELS = 1, MODE_BIG_MODELS = 2, MODE_BVH =
 // the camera rays did through their rings, and hit shading -- the bulk of the instructions -- no longer runs with only
 // the ~25 lanes whose ray happened to hit something in that trip.  Every path executes exactly the operations it
 // executed before, in the same order; only which lane executes them changes.
-template <bool COUNT, int MODE>
+template <bool COUNT, int MODE, bool FUSE>
 __device__ __forceinline__ void render_wavefront(const RenderParams &p, const DevScene &sc, const ShapeTable &tab,
-                                                 float4 *__restrict__ scratch, unsigned long long *__restrict__ cursor,
-                                                 Counters &cnt, unsigned char *smem_raw) {
+                                                 const FrameOut &fo, float4 *__restrict__ scratch,
+                                                 unsigned long long *__restrict__ cursor, Counters &cnt,
+                                                 unsigned char *smem_raw) {
 	const unsigned FULL = 0xffffffffu;
 	constexpr bool MODELS = MODE != MODE_ANALYTIC && MODE != MODE_ANALYTIC_CONST;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -924,25 +1075,34 @@ __device__ __forceinline__ void render_wavefront(const RenderParams &p, const De
 	int ray_head = 0, ray_count = 0, sky_head = 0, sky_count = 0, hit_head = 0, hit_count = 0;  // warp-uniform
 	bool exhausted = false;
 	const vec3 cam_origin = mk(p.c2w[12], p.c2w[13], p.c2w[14]);
+	// fused frame: the ring of completed pixels takes the hit record's triangle word, which scenes without models
+	// do not use; the builds that know models get PIXQ_BYTES more per warp behind the queues
+	PixRing pixq = {MODELS ? reinterpret_cast<uint32_t *>(smem_raw + QUEUE_SMEM_BYTES + warp * PIXQ_BYTES)
+	                       : hitq + (HITQ_WORDS - 1) * QUEUE_SLOTS, 0, 0};
 
 	auto flush_sky = [&](int n) {  // mask *= sky, color += mask (:464-465) for n <= 32 queued records, one per lane
+		unsigned int it = 0;
 		if (lane < n) {
 			const int sl = (sky_head + lane) & (QUEUE_SLOTS - 1);
-			const unsigned int it = __float_as_uint(skyq[0 * QUEUE_SLOTS + sl]);
+			it = __float_as_uint(skyq[0 * QUEUE_SLOTS + sl]);
 			const vec3 c = mk(skyq[1 * QUEUE_SLOTS + sl], skyq[2 * QUEUE_SLOTS + sl], skyq[3 * QUEUE_SLOTS + sl]);
 			vec3 m = mk(skyq[4 * QUEUE_SLOTS + sl], skyq[5 * QUEUE_SLOTS + sl], skyq[6 * QUEUE_SLOTS + sl]);
 			const vec3 dir = mk(skyq[7 * QUEUE_SLOTS + sl], skyq[8 * QUEUE_SLOTS + sl], skyq[9 * QUEUE_SLOTS + sl]);
 			m = m * sky_box(sc, dir);
-			const vec3 r = c + m;
+			// fused frame: a path that ended at a hit travels through this ring as well (marked by d.x = 2, which no
+			// direction -- always the output of normalize(): at most 1 + a few ulp, or 0 / inf / NaN -- can be)
+			const vec3 r = (FUSE && dir.x == 2.0f) ? c : c + m;
 			scratch[it] = make_float4(r.x, r.y, r.z, 0.f);
 		}
 		sky_head = (sky_head + n) & (QUEUE_SLOTS - 1);
 		sky_count -= n;
 		__syncwarp();
+		sample_done<FUSE>(p, fo, scratch, pixq, lane < n, it, lane);
 	};
 
 	for (;;) {
 		bool has_ray = false;
+		bool fin = false;  // fused frame: my path ended at a hit in this trip; its radiance goes out through the sky ring
 		unsigned int item = 0;
 		int bounce = 0;
 		uint32_t seed = 0;
@@ -984,13 +1144,18 @@ __device__ __forceinline__ void render_wavefront(const RenderParams &p, const De
 						done = true;
 					} else {
 						const float4 m1 = __ldg(&sc.materials[4 * material + 1]);
-						scatter(sc, material, pos, n_, front, seed, o, d, mask, m0, m1);
+						scatter<FUSE>(sc, material, pos, n_, front, seed, o, d, mask, m0, m1);
 						bounce += 1;
 						done = false;
 					}
 				}
-				if (done) scratch[item] = make_float4(color.x, color.y, color.z, 0.f);  // summed per pixel in sample order later
-				else has_ray = true;
+				// the sample's radiance, summed per pixel in sample order later.  Fused frame: every finished sample
+				// leaves through the sky ring (ONE site that counts completed samples, with all lanes active): the lane
+				// sits out this trip's scan and pushes {item, radiance} with the escaped paths, marked d.x = 2 (see
+				// flush_sky).  (Keeping such a lane in the scan as a pseudo-ray measured 4 % slower.)
+				if (done && !FUSE) scratch[item] = make_float4(color.x, color.y, color.z, 0.f);
+				if (!done) has_ray = true;
+				fin = FUSE && done;
 			}
 			hit_head = (hit_head + n) & (QUEUE_SLOTS - 1);
 			hit_count -= n;
@@ -998,7 +1163,7 @@ __device__ __forceinline__ void render_wavefront(const RenderParams &p, const De
 		}
 
 		// -- 2. the other lanes take fresh camera rays (start_path, 32 at a time with every lane active)
-		const unsigned need = __ballot_sync(FULL, !has_ray);
+		const unsigned need = __ballot_sync(FULL, !has_ray && !fin);
 		if (need) {
 			const int want = __popc(need);
 			if (ray_count < want && !exhausted) {
@@ -1027,7 +1192,7 @@ __device__ __forceinline__ void render_wavefront(const RenderParams &p, const De
 				exhausted = vm != FULL;
 				__syncwarp();
 			}
-			if (!has_ray) {
+			if (!has_ray && !fin) {
 				const int r = __popc(need & lt_mask);
 				if (r < ray_count) {
 					const int sl = (ray_head + r) & (QUEUE_SLOTS - 1);
@@ -1047,10 +1212,10 @@ __device__ __forceinline__ void render_wavefront(const RenderParams &p, const De
 			ray_count -= popped;
 			__syncwarp();
 		}
-		if (!__any_sync(FULL, has_ray)) {
-			if (hit_count == 0) break;  // nothing in flight: the frame is done for this warp
-			continue;                   // only queued hits are left: the next trip shades them
-		}
+		const bool any_ray = __any_sync(FULL, has_ray || fin);
+		if (!any_ray && hit_count > 0) continue;  // only queued hits are left: the next trip shades them
+		// !any_ray: nothing in flight, the frame is done for this warp once the sky ring is empty (ONE flush site below:
+		// the sky box is the largest block of code in the kernel, and a second inlined copy costs instruction cache)
 
 		// -- 3. closest_intersection for every ray of the trip, :293-378
 		Hit hit = {__int_as_float(0x7f800000), -1, -1};
@@ -1062,7 +1227,7 @@ __device__ __forceinline__ void render_wavefront(const RenderParams &p, const De
 
 		// -- 4. hits -> hit ring (position = origin + direction * t, :311 / :337 / :361); escaped paths -> sky ring
 		const bool is_hit = has_ray && hit.shape >= 0, is_miss = has_ray && hit.shape < 0;
-		const unsigned hm = __ballot_sync(FULL, is_hit), sm = __ballot_sync(FULL, is_miss);
+		const unsigned hm = __ballot_sync(FULL, is_hit), sm = __ballot_sync(FULL, is_miss || fin);
 		if (is_hit) {
 			const vec3 pos = cfma3(d, hit.t, o);
 			const int sl = (hit_head + hit_count + __popc(hm & lt_mask)) & (QUEUE_SLOTS - 1);
@@ -1079,30 +1244,31 @@ __device__ __forceinline__ void render_wavefront(const RenderParams &p, const De
 			hitq[14 * QUEUE_SLOTS + sl] = ((uint32_t)hit.shape << 8) | (uint32_t)bounce;
 			if (MODELS) hitq[15 * QUEUE_SLOTS + sl] = (uint32_t)hit.tri;
 		}
-		if (is_miss) {
+		if (is_miss || fin) {
 			if (COUNT) cnt.sky += 1;
 			const int sl = (sky_head + sky_count + __popc(sm & lt_mask)) & (QUEUE_SLOTS - 1);
 			skyq[0 * QUEUE_SLOTS + sl] = __uint_as_float(item);
 			skyq[1 * QUEUE_SLOTS + sl] = color.x, skyq[2 * QUEUE_SLOTS + sl] = color.y, skyq[3 * QUEUE_SLOTS + sl] = color.z;
 			skyq[4 * QUEUE_SLOTS + sl] = mask.x, skyq[5 * QUEUE_SLOTS + sl] = mask.y, skyq[6 * QUEUE_SLOTS + sl] = mask.z;
-			skyq[7 * QUEUE_SLOTS + sl] = d.x, skyq[8 * QUEUE_SLOTS + sl] = d.y, skyq[9 * QUEUE_SLOTS + sl] = d.z;
+			skyq[7 * QUEUE_SLOTS + sl] = fin ? 2.0f : d.x, skyq[8 * QUEUE_SLOTS + sl] = d.y, skyq[9 * QUEUE_SLOTS + sl] = d.z;
 		}
 		hit_count += __popc(hm);
 		sky_count += __popc(sm);
 		__syncwarp();
-		if (sky_count >= 32) flush_sky(32);
+		if (sky_count >= 32 || (!any_ray && sky_count > 0)) flush_sky(min(sky_count, 32));  // (< 32 are left after a trip)
+		if (!any_ray) break;
 	}
-	if (sky_count > 0) flush_sky(sky_count);
+	if (FUSE && pixq.count > 0) flush_pixels(p, fo, scratch, pixq, pixq.count, lane);
 }
 
 // WF: the queue builds exist with both schedules -- wavefront (hits shaded 32 at a time through the hit ring) for
 // launches that keep every thread busy for many items, plain (hits shaded in place) for short ones, where queueing a
 // hit until 32 are there only lengthens the ragged end (BASELINE config 1, 3 items per thread: +6 % plain) and for
 // launches whose bounce count does not fit the hit record's 8 bits.
-template <bool COUNT, int MODE, bool WF>
+template <bool COUNT, int MODE, bool WF, bool FUSE>
 __global__ void __launch_bounds__(RENDER_THREADS, MODE == MODE_BIG_MODELS ? SRT_MIN_BLOCKS : (MODE == MODE_BVH ? SRT_MIN_BLOCKS_BVH : SRT_MIN_BLOCKS_ANALYTIC))
 render_kernel(const __grid_constant__ RenderParams p, const __grid_constant__ DevScene sc,
-              const __grid_constant__ ShapeTable tab, float4 *__restrict__ scratch,
+              const __grid_constant__ ShapeTable tab, const __grid_constant__ FrameOut fo, float4 *__restrict__ scratch,
               unsigned long long *__restrict__ cursor, Counters *__restrict__ counters) {
 	const unsigned FULL = 0xffffffffu;
 	const int lane = threadIdx.x & 31;
@@ -1115,7 +1281,7 @@ render_kernel(const __grid_constant__ RenderParams p, const __grid_constant__ De
 	// per-warp ring of triangle tiles + one mbarrier per stage
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	if (QUEUES && WF) {  // the wavefront schedule (the loop below is the plain schedule and the dense-sweep build)
-		render_wavefront<COUNT, MODE>(p, sc, tab, scratch, cursor, cnt, smem_raw);
+		render_wavefront<COUNT, MODE, FUSE>(p, sc, tab, fo, scratch, cursor, cnt, smem_raw);
 		if (COUNT) {
 			unsigned long long *c = reinterpret_cast<unsigned long long *>(&cnt);
 			for (int k = 0; k < 6; ++k) {
@@ -1160,12 +1326,18 @@ render_kernel(const __grid_constant__ RenderParams p, const __grid_constant__ De
 	bool exhausted = false;
 	const unsigned lt_mask = (1u << lane) - 1u;
 	const vec3 cam_origin = mk(p.c2w[12], p.c2w[13], p.c2w[14]);
+	// fused frame: ring of completed pixels -- in the (unused) hit-ring space of the plain queue builds, behind the
+	// sweep's shared memory in the dense-sweep build
+	PixRing pixq = {PHASES ? reinterpret_cast<uint32_t *>(smem_raw + RENDER_SMEM_BYTES + BIG_SKYQ_BYTES + warp * PIXQ_BYTES)
+	                       : (SRT_WAVEFRONT ? rayq + (RAYQ_WORDS + SKYQ_WORDS) * QUEUE_SLOTS
+	                                        : reinterpret_cast<uint32_t *>(smem_raw + QUEUE_SMEM_BYTES + warp * PIXQ_BYTES)), 0, 0};
 
 	// evaluate `n` queued sky records (n <= 32), one per lane: mask *= sky, color += mask (:464-465)
 	auto flush_sky = [&](int n) {
+		unsigned int it = 0;
 		if (lane < n) {
 			const int sl = (sky_head + lane) & (QUEUE_SLOTS - 1);
-			const unsigned int it = __float_as_uint(skyq[0 * QUEUE_SLOTS + sl]);
+			it = __float_as_uint(skyq[0 * QUEUE_SLOTS + sl]);
 			const vec3 c = mk(skyq[1 * QUEUE_SLOTS + sl], skyq[2 * QUEUE_SLOTS + sl], skyq[3 * QUEUE_SLOTS + sl]);
 			vec3 m = mk(skyq[4 * QUEUE_SLOTS + sl], skyq[5 * QUEUE_SLOTS + sl], skyq[6 * QUEUE_SLOTS + sl]);
 			const vec3 dir = mk(skyq[7 * QUEUE_SLOTS + sl], skyq[8 * QUEUE_SLOTS + sl], skyq[9 * QUEUE_SLOTS + sl]);
@@ -1176,6 +1348,7 @@ render_kernel(const __grid_constant__ RenderParams p, const __grid_constant__ De
 		sky_head = (sky_head + n) & (QUEUE_SLOTS - 1);
 		sky_count -= n;
 		__syncwarp();
+		sample_done<FUSE>(p, fo, scratch, pixq, lane < n, it, lane);
 	};
 
 	for (;;) {
@@ -1257,9 +1430,13 @@ render_kernel(const __grid_constant__ RenderParams p, const __grid_constant__ De
 				}
 			}
 		}
-		if (!__any_sync(FULL, alive)) break;
+		// nobody alive: the frame is done for this warp once the sky ring is empty (ONE flush site below: the sky box is
+		// the largest block of code in the kernel, and a second inlined copy costs instruction cache)
+		const bool any_alive = __any_sync(FULL, alive);
 
 		bool push_sky = false;
+		bool fin = false;            // my sample finished in this trip (fused frame)
+		unsigned int fin_item = 0;
 		if (alive && park < 0 && !ready) {
 			if (scan_at < 0) {  // new bounce: closest_intersection prologue, :294-297
 				if (COUNT) cnt.bounces += 1;
@@ -1308,7 +1485,7 @@ render_kernel(const __grid_constant__ RenderParams p, const __grid_constant__ De
 							done = true;
 						} else {
 							const float4 m1 = __ldg(&sc.materials[4 * material + 1]);
-							scatter(sc, material, pos, n, front, seed, o, d, mask, m0, m1);
+							scatter<FUSE>(sc, material, pos, n, front, seed, o, d, mask, m0, m1);
 							bounce += 1;
 							done = false;
 						}
@@ -1328,9 +1505,11 @@ render_kernel(const __grid_constant__ RenderParams p, const __grid_constant__ De
 				if (done) {  // the sample's radiance; accumulate_kernel sums a pixel's samples in order (:518-522)
 					scratch[item] = make_float4(color.x, color.y, color.z, 0.f);
 					fresh = true;
+					fin = true, fin_item = item;
 				}
 			}
 		}
+		if (FUSE && __any_sync(FULL, fin)) sample_done<FUSE>(p, fo, scratch, pixq, fin, fin_item, lane);
 
 		if (SKYQ) {  // escaped paths: queue {item, color, mask, direction}; evaluate the sky box 32 at a time
 			const unsigned sm = __ballot_sync(FULL, push_sky);
@@ -1344,9 +1523,10 @@ render_kernel(const __grid_constant__ RenderParams p, const __grid_constant__ De
 				}
 				sky_count += __popc(sm);
 				__syncwarp();
-				if (sky_count >= 32) flush_sky(32);
 			}
+			if (sky_count >= 32 || (!any_alive && sky_count > 0)) flush_sky(min(sky_count, 32));  // (< 32 are left after a trip)
 		}
+		if (!any_alive) break;
 
 		// -- dense triangle phase.  Lane utilisation inside the phase does not depend on how many rays are
 		// parked (the lanes hold triangles there), so it runs after at most PHASE_PATIENCE trips of waiting
@@ -1377,7 +1557,7 @@ render_kernel(const __grid_constant__ RenderParams p, const __grid_constant__ De
 		}
 	}
 
-	if (SKYQ && sky_count > 0) flush_sky(sky_count);
+	if (FUSE && pixq.count > 0) flush_pixels(p, fo, scratch, pixq, pixq.count, lane);
 
 	if (COUNT) {
 		unsigned long long *c = reinterpret_cast<unsigned long long *>(&cnt);
@@ -1415,27 +1595,13 @@ accumulate_kernel(const __grid_constant__ RenderParams p, const float4 *__restri
 	canvas[pix] = c;
 }
 
-// ---- kernel `average`, render.cl:525-535 (aces :473-481) ---------------------------------------
-__device__ __forceinline__ float aces_sqrt(float x) {
-	const float a = 2.51f, b = 0.03f, c = 2.43f, dd = 0.59f, e = 0.14f;
-	float num = x * cfma_(x, a, b);
-	float den = cfma_(x, cfma_(x, c, dd), e);
-	float r = div_(num, den);
-	r = r > 0.0f ? r : 0.0f;  // clamp; NaN -> 0
-	r = r < 1.0f ? r : 1.0f;
-	return sqrt_(r);
-}
+// ---- kernel `average`, render.cl:525-535 (argb_pixel above) ----------------------------------------
 __global__ void __launch_bounds__(256)
 average_kernel(uint32_t num_steps, const float4 *__restrict__ canvas, uchar4 *__restrict__ output, int n) {
 	int id = blockIdx.x * blockDim.x + threadIdx.x;
 	if (id >= n) return;
 	const float steps = (float)num_steps;
-	float4 c = canvas[id];
-	float r = aces_sqrt(div_(c.x, steps)) * 255.0f;
-	float g = aces_sqrt(div_(c.y, steps)) * 255.0f;
-	float b = aces_sqrt(div_(c.z, steps)) * 255.0f;
-	// uchar4(255, r, g, b): A,R,G,B byte order, float -> uchar by truncation
-	output[id] = make_uchar4(255, (unsigned char)(int)r, (unsigned char)(int)g, (unsigned char)(int)b);
+	output[id] = argb_pixel(canvas[id], steps);
 }
 
 // ---- debug: primary hit of every pixel's sample-0 camera ray -----------------------------------

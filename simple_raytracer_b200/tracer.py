@@ -52,6 +52,7 @@ def load_library():
         "srt_set_accel": [vp, i32],
         "srt_set_sweep_filter": [vp, i32],
         "srt_set_schedule": [vp, i32],
+        "srt_set_frame_pipeline": [vp, i32],
         "srt_read_canvas": [vp, vp],
         "srt_write_canvas": [vp, vp],
         "srt_canvas_device_ptr": [vp, pp, ctypes.POINTER(sz)],
@@ -120,6 +121,8 @@ class Tracer:
         self.scene_data = np.zeros(1, SCENE_DATA)
         if os.environ.get("SRT_SWEEP_FILTER"):  # test / tuning hook: "auto", "one", "two" (bit-identical results)
             self.set_sweep_filter(os.environ["SRT_SWEEP_FILTER"])
+        if os.environ.get("SRT_FRAME_PIPELINE"):  # test / tuning hook: "auto", "separate", "fused" (bit-identical results)
+            self.set_frame_pipeline(os.environ["SRT_FRAME_PIPELINE"])
         if os.environ.get("SRT_SCHEDULE"):  # test / tuning hook: "auto", "plain", "wavefront" (bit-identical results)
             self.set_schedule(os.environ["SRT_SCHEDULE"])
 
@@ -207,6 +210,11 @@ class Tracer:
     def set_schedule(self, schedule):
         """srt_set_schedule: "auto" | "plain" | "wavefront" -- how scenes without large models schedule a warp's work."""
         self._check(self._lib.srt_set_schedule(self._h, {"auto": 0, "plain": 1, "wavefront": 2}[schedule]))
+
+    def set_frame_pipeline(self, mode):
+        """srt_set_frame_pipeline: "auto" | "separate" | "fused" -- whether render() accumulates, resolves and reads back
+        inside the render kernel's own run (fused) or as separate steps after it."""
+        self._check(self._lib.srt_set_frame_pipeline(self._h, {"auto": 0, "separate": 1, "fused": 2}[mode]))
 
     def set_sweep_filter(self, mode):
         """srt_set_sweep_filter: "auto" | "one" | "two" -- which conservative filter precedes the exact triangle test."""
