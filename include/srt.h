@@ -200,7 +200,8 @@ int srt_synchronize(srt_tracer *t);
 int srt_debug_primary(srt_tracer *t, const srt_render_data *rd, int32_t *shape_idx, float *t_out);
 /* Same as srt_render, with the work counters of that launch added into *counters (slower). */
 int srt_render_counted(srt_tracer *t, const srt_render_data *rd, srt_counters *counters);
-/* Device math self-test: op 0 log, 1 cos, 2 atan2pi(x,y), 3 pow(x,y), 4 sqrt, 5 schlick(mu=x,cos=y). */
+/* Device math self-test: op 0 log, 1 cos, 2 atan2pi(x,y), 3 pow(x,y), 4 sqrt, 5 schlick(mu=x,cos=y); 6 / 7 = the two
+ * halves of the packed-FP32x2 log of the pair {x, y}, 8 / 9 = of the packed cos (must equal ops 0 / 1 on x and on y). */
 int srt_debug_math(srt_tracer *t, int op, const float *x, const float *y, float *out, size_t n);
 /* FP32 FMA-chain micro-benchmark on the handle's device: achieved TFLOP/s. */
 int srt_measure_fp32_peak(srt_tracer *t, double *tflops, double *sm_clock_mhz_est);

@@ -22,7 +22,7 @@ out = np.zeros(w * h * 4, np.uint8)
 for pinned in (True, False):
     if pinned:
         tr.pin_output(out)
-    for mode in ("separate", "fused", "separate", "fused"):
+    for mode in ("separate", "auto", "fused", "separate", "auto"):
         tr.set_frame_pipeline(mode)
         tr.clear_canvas()
         for k in range(4):

@@ -551,8 +551,8 @@ __device__ __forceinline__ void scatter(const DevScene &sc, int material, vec3 p
 			gz = random_float_normal(seed);
 		}
 	} else {
-		gx = random_float_normal(seed);
-		gy = random_float_normal(seed);
+		const float2 g = random_float_normal_x2(seed);  // two draws as packed FP32x2 chains: fewer issue slots
+		gx = g.x, gy = g.y;
 		gz = random_float_normal(seed);
 	}
 	vec3 rd = normalize(mk(gx, gy, gz));
@@ -1595,6 +1595,44 @@ accumulate_kernel(const __grid_constant__ RenderParams p, const float4 *__restri
 	canvas[pix] = c;
 }
 
+// ---- frame epilogue: accumulate_kernel + kernel `average` + the read-back in ONE kernel ---------------------------
+// For srt_render_frame into a page-locked caller vector (srt_pin_output): one thread per FOUR consecutive local pixels
+// performs accumulate_kernel's additions for them, applies `average` (render.cl:525-535) and stores the four ARGB8
+// pixels as one 16-byte word both to the device image and straight into the caller's vector over PCIe (a warp writes
+// 512 contiguous bytes), so no copy engine transfer follows the kernels.  Same arithmetic, same order: bit-identical.
+__global__ void __launch_bounds__(256)
+frame_epilogue_kernel(const __grid_constant__ RenderParams p, const float4 *__restrict__ scratch, float4 *__restrict__ canvas,
+                      uchar4 *__restrict__ output, uchar4 *__restrict__ host_out, uint32_t num_steps) {
+	const unsigned int q = blockIdx.x * blockDim.x + threadIdx.x;  // quad of pixels (full frame: local pixel == pixel id)
+	const unsigned int first = 4u * q;
+	if (first >= p.total_pixels) return;
+	const float steps = (float)num_steps, ns_f = (float)p.num_samples;
+	uchar4 px[4];
+	const int n = min(4u, p.total_pixels - first);
+	for (int j = 0; j < n; ++j) {
+		const size_t pix = (size_t)first + j;
+		float4 c = canvas[pix];
+		const float4 *s = scratch + pix * p.num_samples;
+		vec3 color = mk(0, 0, 0);
+		for (int k = 0; k < p.num_samples; ++k) color = color + xyz(s[k]);
+		if (p.inv_ns != 0.0f) {
+			c.x += color.x * p.inv_ns, c.y += color.y * p.inv_ns, c.z += color.z * p.inv_ns;
+		} else {
+			c.x += div_(color.x, ns_f), c.y += div_(color.y, ns_f), c.z += div_(color.z, ns_f);
+		}
+		canvas[pix] = c;
+		px[j] = argb_pixel(c, steps);
+	}
+	if (n == 4) {  // total_pixels * 4 bytes: both images are 16-byte aligned at every quad
+		const uint4 w = make_uint4(*reinterpret_cast<uint32_t *>(&px[0]), *reinterpret_cast<uint32_t *>(&px[1]),
+		                           *reinterpret_cast<uint32_t *>(&px[2]), *reinterpret_cast<uint32_t *>(&px[3]));
+		reinterpret_cast<uint4 *>(output)[q] = w;
+		reinterpret_cast<uint4 *>(host_out)[q] = w;
+	} else {
+		for (int j = 0; j < n; ++j) output[first + j] = px[j], host_out[first + j] = px[j];
+	}
+}
+
 // ---- kernel `average`, render.cl:525-535 (argb_pixel above) ----------------------------------------
 __global__ void __launch_bounds__(256)
 average_kernel(uint32_t num_steps, const float4 *__restrict__ canvas, uchar4 *__restrict__ output, int n) {
@@ -1714,6 +1752,11 @@ __global__ void math_kernel(int op, const float *__restrict__ x, const float *__
 	case 3: r = pow_(x[i], y[i]); break;
 	case 4: r = sqrt_(x[i]); break;
 	case 5: r = schlick_(x[i], y[i]); break;
+	// the packed FP32x2 forms of random_float_normal_x2: op 6/7 = halves of log_x2({x, y}), 8/9 = halves of cos_x2({x, y})
+	case 6: r = log_x2(make_float2(x[i], y[i])).x; break;
+	case 7: r = log_x2(make_float2(x[i], y[i])).y; break;
+	case 8: r = cos_x2(make_float2(x[i], y[i])).x; break;
+	case 9: r = cos_x2(make_float2(x[i], y[i])).y; break;
 	}
 	out[i] = r;
 }

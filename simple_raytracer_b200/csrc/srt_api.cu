@@ -68,6 +68,7 @@ struct srt_tracer {
 	uchar4 *output = nullptr;  // ARGB8 (tracer.cpp:40)
 	uint8_t *pinned_out = nullptr;   // staging buffer of every read-back into memory the library does not own
 	void *registered_out = nullptr;  // srt_pin_output: a caller buffer page-locked at the CALLER's request
+	uint8_t *registered_dev = nullptr;  // the same memory as the device sees it (null: not mapped)
 	size_t registered_bytes = 0;
 	cudaEvent_t chunk_ev[4] = {nullptr, nullptr, nullptr, nullptr};  // read-back pipeline (read_back)
 	float4 *sky = nullptr;
@@ -104,6 +105,10 @@ struct srt_tracer {
 	// fused frame (srt_render_frame, srt::FrameOut): completion counters, the band flags the kernel publishes in
 	// host-mapped memory, and the second stream the bands' read-backs run on while the frame is still being traced
 	int frame_pipeline = SRT_FRAME_AUTO;  // srt_set_frame_pipeline
+	// set for the duration of one srt_render_frame into the pinned caller vector: the launch's epilogue is
+	// frame_epilogue_kernel (accumulate + average + store to the host) instead of accumulate_kernel
+	uchar4 *epilogue_host = nullptr;
+	uint32_t epilogue_steps = 0;
 	unsigned int *pix_done = nullptr, *row_done = nullptr, *band_done = nullptr;
 	unsigned int *host_flags = nullptr;
 	unsigned int frame_epoch = 0;
@@ -259,7 +264,11 @@ int launch_render_impl(srt_tracer *t, const srt::RenderParams &p, const srt::Fra
 	cudaError_t le = cudaEventRecord(ev.first, t->stream);
 	kernel<<<grid, srt::RENDER_THREADS, smem, t->stream>>>(p, sc, t->shape_table, FUSE ? *fo : srt::FrameOut{}, t->scratch.ptr,
 	                                                        t->cursor, t->counters);
-	if (!FUSE) srt::accumulate_kernel<<<(p.total_pixels + 255) / 256, 256, 0, t->stream>>>(p, t->scratch.ptr, t->canvas);
+	if (!FUSE && t->epilogue_host)
+		srt::frame_epilogue_kernel<<<((p.total_pixels + 3) / 4 + 255) / 256, 256, 0, t->stream>>>(p, t->scratch.ptr, t->canvas, t->output,
+		                                                                                        t->epilogue_host, t->epilogue_steps);
+	else if (!FUSE)
+		srt::accumulate_kernel<<<(p.total_pixels + 255) / 256, 256, 0, t->stream>>>(p, t->scratch.ptr, t->canvas);
 	if (le == cudaSuccess) le = cudaEventRecord(ev.second, t->stream);
 	if (le == cudaSuccess) le = cudaGetLastError();
 	if (le != cudaSuccess) {
@@ -673,13 +682,19 @@ int srt_pin_output(srt_tracer *t, void *buffer, size_t bytes) {
 	SRT_BIND(t);
 	if (!buffer || bytes == 0) return fail(t, SRT_ERR_INVALID, "srt_pin_output: null buffer");
 	if (int rc = srt_unpin_output(t)) return rc;
-	cudaError_t e = cudaHostRegister(buffer, bytes, cudaHostRegisterDefault);
+	cudaError_t e = cudaHostRegister(buffer, bytes, cudaHostRegisterMapped);
 	if (e != cudaSuccess) {
 		cudaGetLastError();  // not sticky: the staging path keeps working
 		return fail(t, SRT_ERR_CUDA, "cudaHostRegister failed: %s", cudaGetErrorString(e));
 	}
 	t->registered_out = buffer;
 	t->registered_bytes = bytes;
+	void *dev = nullptr;  // mapped into the device's address space: srt_render_frame's epilogue stores the image into it
+	if (cudaHostGetDevicePointer(&dev, buffer, 0) != cudaSuccess) {
+		cudaGetLastError();
+		dev = nullptr;  // copies still work
+	}
+	t->registered_dev = static_cast<uint8_t *>(dev);
 	return SRT_OK;
 }
 
@@ -689,6 +704,7 @@ int srt_unpin_output(srt_tracer *t) {
 	SRT_CUDA(t, cudaStreamSynchronize(t->stream));
 	cudaError_t e = cudaHostUnregister(t->registered_out);
 	t->registered_out = nullptr;
+	t->registered_dev = nullptr;
 	t->registered_bytes = 0;
 	if (e != cudaSuccess) {
 		cudaGetLastError();
@@ -801,6 +817,19 @@ int srt_render_frame(srt_tracer *t, const srt_render_data *rd, uint32_t ticks_st
 	const bool worth = p.num_samples <= 2 && !t->has_big_models;
 	const bool fused = can_fuse && (t->frame_pipeline == SRT_FRAME_FUSED || (t->frame_pipeline == SRT_FRAME_AUTO && worth));
 	if (fused) return render_frame_fused(t, p, ticks_stopped, argb_out);
+	// a full frame into the page-locked caller vector: one epilogue kernel accumulates, resolves and stores the image
+	// into the caller's memory directly (no separate `average` launch, no copy-engine transfer after it)
+	const bool direct = t->registered_out && argb_out >= (uint8_t *)t->registered_out &&
+	                    argb_out + (size_t)t->width * t->height * 4 <= (uint8_t *)t->registered_out + t->registered_bytes;
+	if (t->frame_pipeline != SRT_FRAME_SEPARATE && can_fuse && direct && t->registered_dev && ((uintptr_t)argb_out & 15) == 0) {
+		t->epilogue_host = reinterpret_cast<uchar4 *>(t->registered_dev + (argb_out - (uint8_t *)t->registered_out));
+		t->epilogue_steps = ticks_stopped;
+		const int rc = launch_params<false>(t, p);
+		t->epilogue_host = nullptr;
+		if (rc) return rc;
+		SRT_CUDA(t, cudaStreamSynchronize(t->stream));
+		return SRT_OK;
+	}
 	if (int rc = srt_render(t, rd)) return rc;
 	return srt_resolve(t, ticks_stopped, argb_out);
 }

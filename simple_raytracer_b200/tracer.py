@@ -101,7 +101,8 @@ class _CudaView:
 
 
 class Tracer:
-    MATH_OPS = {"log": 0, "cos": 1, "atan2pi": 2, "pow": 3, "sqrt": 4, "schlick": 5}
+    MATH_OPS = {"log": 0, "cos": 1, "atan2pi": 2, "pow": 3, "sqrt": 4, "schlick": 5,
+                "log_x2_lo": 6, "log_x2_hi": 7, "cos_x2_lo": 8, "cos_x2_hi": 9}
 
     def __init__(self, width, height, skybox, device=-1):
         self._lib = load_library()

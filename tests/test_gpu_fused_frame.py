@@ -67,6 +67,32 @@ def test_fused_frames_of_random_scenes_against_the_reference_kernel(sky, oracle_
     tr.close()
 
 
+@pytest.mark.parametrize("cfg,w,h", [(1, 203, 151), (2, 320, 97), (3, 161, 120), (2, 1, 1), (2, 1920, 1080)])
+@pytest.mark.parametrize("ns", [3, 4])
+def test_frame_epilogue_into_the_pinned_vector_equals_separate_steps(sky, cfg, w, h, ns):
+    """A frame of more than 2 spp into the page-locked caller vector runs accumulate + average + the store into the
+    caller's memory as ONE epilogue kernel (frame_epilogue_kernel, 16-byte stores over PCIe; pixel counts that are
+    not a multiple of four take the tail branch).  Images of every frame, the device image and the canvas must equal
+    the separate steps; an unpinned vector, and a view at an offset inside the pinned one, keep working."""
+    sc = scenes.CONFIGS[cfg](w, h)
+    tr = make_tracer(sc, sky)
+    big = np.zeros(w * h * 4 + 64, np.uint8)
+    tr.pin_output(big)
+    out = big[16:16 + w * h * 4].reshape(h, w, 4)  # 16-byte aligned inside the pinned range: the epilogue path
+    got_canvas, got = frames(tr, sc, 3, out, num_samples=ns)
+    dev_img = tr.read_output()
+    odd = big[4:4 + w * h * 4].reshape(h, w, 4)    # not 16-byte aligned: copy-engine path
+    _, got_odd = frames(tr, sc, 3, odd, num_samples=ns)
+    tr.set_frame_pipeline("separate")
+    want_canvas, want = frames(tr, sc, 3, out, num_samples=ns)
+    tr.unpin_output()
+    assert_bit_equal(want_canvas, got_canvas, "canvas")
+    for k in range(3):
+        assert np.array_equal(want[k], got[k]) and np.array_equal(want[k], got_odd[k]), f"image of frame {k}"
+    assert np.array_equal(dev_img, want[2])
+    tr.close()
+
+
 @pytest.mark.parametrize("pinned", [False, True])
 def test_fused_frame_at_1080p_and_4k(sky, pinned):
     """Full BASELINE frame sizes (32 bands of 34 / 68 rows), the caller's vector page-locked or not."""

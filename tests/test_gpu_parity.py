@@ -125,6 +125,26 @@ def test_device_math_bit_exact(ctx, op):
     assert_bit_equal(ctx["oracle"].math(op, x, y), tr.debug_math(op, x, y), op)
 
 
+@pytest.mark.parametrize("fn", ["log", "cos"])
+def test_packed_fp32x2_math_equals_the_scalar_functions(ctx, fn):
+    """random_float_normal_x2 evaluates log and cos for two draws in lock step with FADD2 / FMUL2 / FFMA2; each half
+    must be the scalar device function -- and so the oracle's -- bit for bit, whatever sits in the other half
+    (pairs are drawn independently, so the two halves take different polynomial branches)."""
+    rng = np.random.default_rng(7)
+    n = 1 << 20
+    if fn == "log":
+        a = rng.integers(0, 2 ** 32, size=n, dtype=np.uint64).astype(np.float32) / np.float32(4294967296.0)
+        b = rng.integers(0, 2 ** 32, size=n, dtype=np.uint64).astype(np.float32) / np.float32(4294967296.0)
+        a[:4], b[:4] = [0.0, 1.0, 2.0 ** -32, 0.5], [0.7, 0.0, 0.0, 2.0 ** -32]
+    else:
+        a = (np.float32(6.28318530717958647692) * rng.random(n).astype(np.float32)).astype(np.float32)
+        b = (np.float32(6.28318530717958647692) * rng.random(n).astype(np.float32)).astype(np.float32)
+        a[:2], b[:2] = [0.0, 6.2831855], [6.2831855, 0.0]
+    tr = make_tracer(scenes.config1(16, 16), ctx["sky"])
+    assert_bit_equal(ctx["oracle"].math(fn, a), tr.debug_math(fn + "_x2_lo", a, b), fn + " low half")
+    assert_bit_equal(ctx["oracle"].math(fn, b), tr.debug_math(fn + "_x2_hi", a, b), fn + " high half")
+
+
 @pytest.mark.parametrize("cfg", [1, 2, 3])
 def test_golden_fixture(cfg):
     """Committed oracle output (tests/golden/make_golden.py) reproduced by the CUDA path from the
