@@ -369,8 +369,10 @@ __device__ __forceinline__ int scan_shapes(const DevScene &sc, vec3 o, vec3 d, v
 		if (hdr.x == SHAPE_SPHERE) {
 			// intersect_sphere, :180-204
 			vec3 L = xyz(a) - o;
-			float b = dot(L, d);
-			float c = cfma_(-a.w, a.w, dot(L, L));
+			// dot(L, d) and dot(L, L) as ONE packed FP32x2 chain (each half is the scalar dot's FMUL, FFMA, FFMA)
+			const float2 bl = dot_x2(L, d, L);
+			float b = bl.x;
+			float c = cfma_(-a.w, a.w, bl.y);
 			float disc = cfma_(b, b, -c);
 			if (disc >= 0.0f) {
 				float sq = sqrt_(disc);
@@ -385,9 +387,11 @@ __device__ __forceinline__ int scan_shapes(const DevScene &sc, vec3 o, vec3 d, v
 			// intersect_plane, :206-221
 			const float4 nb = CONST ? tab->b[i] : __ldg(&sc.shape_b[i]);
 			vec3 n = xyz(nb);
-			float denom = dot(n, d);
+			// dot(n, d) and dot(n, p0 - o) as one packed chain (the second is only used when the first is not zero)
+			const float2 dn = dot_x2(n, d, xyz(a) - o);
+			float denom = dn.x;
 			if (fabsf(denom) != 0.0f) {
-				float t = div_(dot(n, xyz(a) - o), denom);
+				float t = div_(dn.y, denom);
 				if (t >= 0.0f && t < hit.t) {
 					hit.t = t;
 					hit.shape = i;
@@ -509,9 +513,12 @@ __device__ __forceinline__ vec3 sky_box(const DevScene &sc, vec3 d) {
 	const float4 t01 = __ldg(&sc.sky[(size_t)j1 * w + i0]);
 	const float4 t11 = __ldg(&sc.sky[(size_t)j1 * w + i1]);
 	float w00 = (1.0f - a) * (1.0f - b), w10 = a * (1.0f - b), w01 = (1.0f - a) * b, w11 = a * b;
-	vec3 tex = mk(fma_(w11, t11.x, fma_(w01, t01.x, fma_(w10, t10.x, w00 * t00.x))),
-	              fma_(w11, t11.y, fma_(w01, t01.y, fma_(w10, t10.y, w00 * t00.y))),
-	              fma_(w11, t11.z, fma_(w01, t01.z, fma_(w10, t10.z, w00 * t00.z))));
+	// red and green as one packed FP32x2 chain (the texels' .xy arrive as register pairs from the 16-byte loads)
+	const float2 rg = __ffma2_rn(make_float2(w11, w11), make_float2(t11.x, t11.y),
+	                             __ffma2_rn(make_float2(w01, w01), make_float2(t01.x, t01.y),
+	                                        __ffma2_rn(make_float2(w10, w10), make_float2(t10.x, t10.y),
+	                                                   __fmul2_rn(make_float2(w00, w00), make_float2(t00.x, t00.y)))));
+	vec3 tex = mk(rg.x, rg.y, fma_(w11, t11.z, fma_(w01, t01.z, fma_(w10, t10.z, w00 * t00.z))));
 	return tex + sun;
 }
 
@@ -556,9 +563,10 @@ __device__ __forceinline__ void scatter(const DevScene &sc, int material, vec3 p
 		gz = random_float_normal(seed);
 	}
 	vec3 rd = normalize(mk(gx, gy, gz));
-	rd = rd * sign_(dot(n, rd));
+	const float2 nn = dot_x2(n, rd, d);                         // {dot(n, rd), dot(n, d)}: one packed chain
+	rd = rd * sign_(nn.x);
 	vec3 random_dir = normalize(n + rd);                       // :421
-	float k2 = 2.0f * dot(d, n);                                // reflect, :139-141
+	float k2 = 2.0f * nn.y;                                     // reflect, :139-141: 2 dot(d, n) (products commute exactly)
 	vec3 reflected = mk(cfma_(-k2, n.x, d.x), cfma_(-k2, n.y, d.y), cfma_(-k2, n.z, d.z));
 	const bool is_metallic = m0.y > random_float(seed);         // :424
 	const bool is_specular = m0.z > random_float(seed);         // :425

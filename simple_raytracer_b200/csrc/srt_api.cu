@@ -811,11 +811,11 @@ int srt_render_frame(srt_tracer *t, const srt_render_data *rd, uint32_t ticks_st
 	// the fused pass needs a full frame with work in it; tile-sharded launches (srt_set_row_bands) and empty ones
 	// (render.cl:403: zero bounces add zero radiance) take the separate kernels
 	const bool can_fuse = t->band_n <= 1 && p.num_bounces > 0 && p.total_items > 0;
-	// AUTO: the in-kernel resolve costs the render kernel ~11 % (1080p, BASELINE config 2: +8.5 % instructions, a release
-	// fence per 32 finished samples) and hides ~0.19 ms of resolve + read-back, so it pays for frames of few samples per
-	// pixel (measured: 1 spp +9 %, 2 spp +1.5 %, 4 spp +-0, 8 spp -1.6 %; dense-sweep scenes -1.3 %)
-	const bool worth = p.num_samples <= 2 && !t->has_big_models;
-	const bool fused = can_fuse && (t->frame_pipeline == SRT_FRAME_FUSED || (t->frame_pipeline == SRT_FRAME_AUTO && worth));
+	// The fused pass is opt-in (SRT_FRAME_FUSED): its in-kernel resolve costs the render kernel ~11 % (1080p, BASELINE
+	// config 2: +8.5 % instructions, a release increment per finished sample) and hides ~0.14 ms of resolve + read-back:
+	// measured against the separate steps it is +2..9 % at 1 spp, +-3 % at 2 spp, -2..-4 % from 4 spp up and on
+	// dense-sweep scenes -- within run-to-run noise where it wins, so AUTO does not pick it
+	const bool fused = can_fuse && t->frame_pipeline == SRT_FRAME_FUSED;
 	if (fused) return render_frame_fused(t, p, ticks_stopped, argb_out);
 	// a full frame into the page-locked caller vector: one epilogue kernel accumulates, resolves and stores the image
 	// into the caller's memory directly (no separate `average` launch, no copy-engine transfer after it)
