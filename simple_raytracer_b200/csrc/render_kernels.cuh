@@ -154,9 +154,9 @@ constexpr int INLINE_MODEL_TRIS = 32;
 // DESIGN.md "Triangle filter").  Everything that survives runs tri_exact, the reference arithmetic.
 __device__ __forceinline__ bool tri_filter(const float4 v0, const float4 e1, const float4 e2, vec3 o, vec3 d) {
 	vec3 h = cross(d, xyz(e2));
-	float det = dot(xyz(e1), h);
 	vec3 s = o - xyz(v0);
-	float su = dot(s, h);
+	const float2 ds = dot_x2(h, xyz(e1), s);  // {dot(e1, h), dot(s, h)} as one packed chain (products commute exactly)
+	float det = ds.x, su = ds.y;
 	float x = __int_as_float(__float_as_int(su) ^ (__float_as_int(det) & 0x80000000));
 	float lim = fabsf(det) * 1.000001f;
 	return !(x > lim || x < -1e-6f);
@@ -164,17 +164,21 @@ __device__ __forceinline__ bool tri_filter(const float4 v0, const float4 e1, con
 __device__ __forceinline__ void tri_exact(const float4 v0, const float4 e1, const float4 e2, vec3 o, vec3 d, int shape,
                                           int tri, Hit &hit) {
 	vec3 h = cross(d, xyz(e2));
-	float det = dot(xyz(e1), h);
+	vec3 s = o - xyz(v0);
+	// the four dot products as two packed FP32x2 chains: {e1.h, s.h} and {d.q, e2.q} (products commute exactly, the
+	// accumulation order x, y, z is dot()'s)
+	const float2 ds = dot_x2(h, xyz(e1), s);
+	float det = ds.x;
 	// det == 0 (render.cl:253) needs no test of its own: then f = +-inf and t below is +-inf or NaN,
 	// which can never satisfy t < hit.t
 	float f = rcp_(det);
-	vec3 s = o - xyz(v0);
-	float u = f * dot(s, h);
+	float u = f * ds.y;
 	if (u < 0.0f || u > 1.0f) return;
 	vec3 q = cross(s, xyz(e1));
-	float v = f * dot(d, q);
+	const float2 dq = dot_x2(q, d, xyz(e2));
+	float v = f * dq.x;
 	if (v < 0.0f || u + v > 1.0f) return;
-	float t = f * dot(xyz(e2), q);
+	float t = f * dq.y;
 	if (t > 0.0f && t < hit.t) {
 		hit.t = t;
 		hit.shape = shape;
