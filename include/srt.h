@@ -143,19 +143,14 @@ int srt_pin_output(srt_tracer *t, void *buffer, size_t bytes);
 int srt_unpin_output(srt_tracer *t);
 
 /* Tracer::render(ticks_stopped, output), tracer.cpp:103-116, in one call.  The result -- canvas and image -- is what
- * srt_render followed by srt_resolve produces, bit for bit, whichever way the frame is executed:
- *   SRT_FRAME_SEPARATE  the three steps one after the other (render kernel + accumulate, average, blocking copy);
- *   SRT_FRAME_FUSED     ONE pass: the render kernel itself adds each pixel's samples to the canvas the moment the pixel's
- *                       last sample finishes, applies `average` to it, and publishes finished bands of rows through
- *                       host-mapped flags; this call polls them and starts each band's device-to-host copy on a second
- *                       stream while the rest of the frame is still being traced, so the blocking read-back of
- *                       tracer.cpp:115 hides behind the kernel (1080p: 8.3 MB, 0.16 ms).  The in-kernel bookkeeping
- *                       costs the render kernel ~11 %;
- *   SRT_FRAME_AUTO      (default) fused for frames of at most 2 samples per pixel in scenes without large meshes
- *                       (measured +9 % at 1 spp, +1.5 % at 2 spp), separate otherwise.
- * Launches restricted by srt_set_row_bands and launches without work always take the separate steps. */
+ * srt_render followed by srt_resolve produces, bit for bit.  When argb_out lies (16-byte aligned) inside the vector
+ * the caller page-locked with srt_pin_output and the launch covers the full frame, the steps after the render kernel --
+ * the per-pixel sum of the samples, `average`, the read-back -- run as ONE epilogue kernel that stores the ARGB8 image
+ * straight into the caller's memory (16-byte stores over PCIe at the copy engine's rate; no separate `average` launch,
+ * no copy-engine transfer).  Otherwise, and always with SRT_FRAME_SEPARATE (parity tests compare the two), the
+ * separate steps run: render kernel + accumulate, average, copy through the handle's pinned staging buffer. */
 int srt_render_frame(srt_tracer *t, const srt_render_data *rd, uint32_t ticks_stopped, uint8_t *argb_out);
-enum { SRT_FRAME_AUTO = 0, SRT_FRAME_SEPARATE = 1, SRT_FRAME_FUSED = 2 };
+enum { SRT_FRAME_AUTO = 0, SRT_FRAME_SEPARATE = 1 };
 int srt_set_frame_pipeline(srt_tracer *t, int mode);
 
 /* Restrict rendering to interleaved row bands (tile sharding across GPUs): only rows y with

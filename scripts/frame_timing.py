@@ -1,5 +1,5 @@
 """Developer timing of Tracer.render (srt_render_frame) per frame: wall clock and the render kernel's own duration
-(CUDA events), separate steps vs fused pass, BASELINE config 2 at 1080p (pinned output)."""
+(CUDA events), separate steps vs the epilogue into the pinned vector (auto), BASELINE config 2 at 1080p (pinned output)."""
 import os
 import sys
 import time
@@ -22,7 +22,7 @@ out = np.zeros(w * h * 4, np.uint8)
 for pinned in (True, False):
     if pinned:
         tr.pin_output(out)
-    for mode in ("separate", "auto", "fused", "separate", "auto"):
+    for mode in ("separate", "auto", "separate", "auto"):
         tr.set_frame_pipeline(mode)
         tr.clear_canvas()
         for k in range(4):

@@ -33,6 +33,10 @@ __global__ void __launch_bounds__(128) k(float *out, const float *in) {
 				if (MODE == 5) c2[i] = __ffma2_rn(u2, b2[i], c2[i]);      // packed, one pair shared
 				if (MODE == 6) { c2[i] = __ffma2_rn(u2, b2[i], c2[i]); c[i] = __fmaf_rn(u, b[i], c[i]); a[i] = __fmaf_rn(v, b[i], a[i]); }  // 1 packed : 2 scalar
 				if (MODE == 7) { c2[i] = __ffma2_rn(u2, b2[i], c2[i]); c[i] = __fmaf_rn(u, b[i], c[i]); }  // 1 packed : 1 scalar
+				// packed with ONE SCALAR operand broadcast to both halves (SASS operand form R.F32)
+				if (MODE == 8) c2[i] = __ffma2_rn(a2[i], make_float2(b[i], b[i]), c2[i]);   // pair, scalar, pair: all distinct
+				if (MODE == 9) c2[i] = __ffma2_rn(a2[i], make_float2(u, u), c2[i]);         // distinct pair, shared scalar
+				if (MODE == 10) c2[i] = __ffma2_rn(u2, make_float2(b[i], b[i]), c2[i]);     // shared pair, distinct scalar
 			}
 		}
 	}
@@ -77,6 +81,9 @@ int main() {
 		run<5>("FFMA2 1 shared pair", N, w, out, in, mhz);
 		run<6>("mix 1 FFMA2 : 2 FFMA", 3 * N, w, out, in, mhz);
 		run<7>("mix 1 FFMA2 : 1 FFMA", 2 * N, w, out, in, mhz);
+		run<8>("FFMA2 pair, scalar bcast, pair", N, w, out, in, mhz);
+		run<9>("FFMA2 pair, SHARED scalar bcast", N, w, out, in, mhz);
+		run<10>("FFMA2 SHARED pair, scalar bcast", N, w, out, in, mhz);
 	}
 	return 0;
 }

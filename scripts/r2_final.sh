@@ -26,10 +26,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-fil
 scripts/ncu_capture.sh 2 ${T}_prof_c2 16 - batch
 scripts/ncu_capture.sh 3 ${T}_prof_c3 2
 scripts/ncu_capture.sh 5 ${T}_prof_c5 2
-# frame pipelines (srt_render_frame): separate steps / epilogue into the pinned vector (auto, > 2 spp) / fused pass
-for a in "2 1" "2 2" "2 4" "2 8" "1 1" "3 4"; do python scripts/frame_timing.py $a 2>&1 | head -3; done > gpurun_out/${T}_frame_pipelines.txt; cat gpurun_out/${T}_frame_pipelines.txt
-# the fused-frame build of the render kernel under ncu (key metrics only)
-python scripts/profile_frame.py 2 3 fused && ncu --set full --import-source on --clock-control none -k regex:render_kernel -s 2 -c 1 -f \
-    -o gpurun_out/${T}_prof_frame_fused python scripts/profile_frame.py 2 3 fused > gpurun_out/${T}_ncu_frame_fused.log 2>&1; tail -1 gpurun_out/${T}_ncu_frame_fused.log
+# frame pipelines (srt_render_frame): separate steps / epilogue into the pinned vector (auto)
+for a in "2 1" "2 2" "2 4" "2 8" "1 1" "3 4"; do python scripts/frame_timing.py $a 2>&1 | head -4; done > gpurun_out/${T}_frame_pipelines.txt; cat gpurun_out/${T}_frame_pipelines.txt
 # the whole GPU suite once more on the build with device-side invariant checks
 if [ -f build/variants/libsrt_checks.so ]; then ( SRT_LIB=$PWD/build/variants/libsrt_checks.so timeout 1500 python -m pytest tests -m gpu -q -x ) > gpurun_out/${T}_pytest_gpu_checks.log 2>&1; echo "checks rc=$?"; tail -2 gpurun_out/${T}_pytest_gpu_checks.log; fi

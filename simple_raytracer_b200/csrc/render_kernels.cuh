@@ -101,29 +101,6 @@ struct RenderParams {
 	int uv_max_tris;           // models of at most this many triangles are swept with the two-strip filter
 };
 
-// Fused frame (srt_render_frame, FUSE builds of render_kernel): everything the reference's Tracer::render does after
-// the `render` launch -- `canvas[id] += color` (render.cl:520-522), kernel `average` (:525-535) and the blocking
-// read of the ARGB8 image (src/tracer.cpp:110-115) -- happens WHILE the frame is still being traced.  The lane that
-// finishes the last sample of a pixel (a per-pixel counter) queues the pixel; the warp resolves 32 queued pixels at a
-// time: samples summed in sample order from scratch (still in L2), canvas updated, ARGB8 written.  Finished rows are
-// counted per band of rows, and the lane that completes a band publishes it in host-mapped memory; the host thread
-// inside srt_render_frame polls those flags and starts the band's device-to-host copy on a second stream at once, so
-// that when the kernel ends only the last band's copy is outstanding (a 1080p frame: 0.16 ms of read-back hidden).
-// The additions are the ones accumulate_kernel + average_kernel perform, in the same order: bit-identical images.
-constexpr int FRAME_MAX_BANDS = 64;
-struct FrameOut {
-	float4 *canvas;
-	uchar4 *output;
-	unsigned int *pix_done;   // per pixel: samples finished in this launch (reset to 0 by the lane that completes it)
-	unsigned int *row_done;   // per row: pixels resolved (reset likewise)
-	unsigned int *band_done;  // per band: rows resolved (reset likewise)
-	volatile unsigned int *host_flags;  // host-mapped, per band: frame epoch of the last completed frame
-	unsigned int epoch;
-	unsigned int num_steps;   // kernel `average`'s argument (ticks_stopped, src/tracer.cpp:111)
-	int band_rows;            // rows per band
-	int ns_shift;             // log2(num_samples) when that is a power of two, else -1
-};
-
 struct Counters {
 	unsigned long long samples, bounces, tri_tests, aabb_pass, hits, sky;
 };
@@ -213,31 +190,34 @@ struct TriFlt {
 // The margin is formed once per triangle and tile from the LARGEST R among the parked rays (M = g * Rmax + 2e-6):
 // a larger margin only lets more triangles through.
 // m: the margin M of this triangle for the phase (g * Rmax + 2e-6, formed once per tile); cz = r2.x
-#ifndef SRT_PACKED_SLOTS  // how many of a lane's TRIS_PER_LANE triangle slots evaluate {det, t} as a packed FP32x2 chain
-#define SRT_PACKED_SLOTS 4
-#endif
-// packed: a compile-time constant at every call site (the slot loop is unrolled)
-__device__ __forceinline__ bool tri_filter_sweep(const TriFlt &r, const float m, const float4 r0, const float4 r1,
-                                                 const float cz, const bool packed) {
-	// {det, t} = d.x {n'.x, m.x} + d.y {n'.y, m.y} + d.z {n'.z, m.z}
-	float det, t;
-	if (packed) {
-		const float2 dt = __ffma2_rn(make_float2(r1.x, r1.y), r.c,
-		                             __ffma2_rn(make_float2(r0.z, r0.w), r.b, __fmul2_rn(make_float2(r0.x, r0.y), r.a)));
-		det = dt.x, t = dt.y;
-	} else {  // the same operations, one half at a time: bit-identical
-		det = fma_(r1.x, r.c.x, fma_(r0.z, r.b.x, r0.x * r.a.x));
-		t = fma_(r1.x, r.c.y, fma_(r0.z, r.b.y, r0.x * r.a.y));
-	}
-	const float su = fma_(r.f.x, cz, fma_(r.e.y, r1.w, fma_(r.e.x, r1.z, -t)));
+// The sweep evaluates the filter for TWO RAYS at once: every floating-point operation below is one packed FP32x2
+// instruction whose halves belong to ray A and ray B, with the ray operands as register pairs {A, B} (loop-invariant over
+// a lane's triangles) and the triangle operand as ONE scalar register broadcast to both halves (SASS operand form
+// `R.F32`).  That is the cheapest form an FMA can take on this machine: scripts/microbench/fma_operands.cu measures 2.16
+// cycles per FFMA2 (1.08 per FMA) for {shared pair, broadcast scalar, accumulator pair} against 1.31 for a scalar FFMA
+// with one shared operand, 3.05 for an FFMA2 of three distinct pairs -- and 2.8 per instruction when packed and scalar
+// FMAs alternate, which is what the previous form of this loop ({det, t} packed per ray, the rest scalar) did.
+// Each half performs exactly the operations the scalar filter performed, in the same order, so its decisions -- and the
+// bound derived in DESIGN 4.1, restated operation for operation in oracle/filter_check.c -- are unchanged.
+__device__ __forceinline__ float2 bc(float x) { return make_float2(x, x); }
+struct RayPair {  // the operands of two parked rays, interleaved: {A, B} per component; c = o x d
+	float2 dx, dy, dz, cx, cy, cz;
+};
+// m: the margin M of this triangle for the phase (g * Rmax + 2e-6, formed once per tile).
+// Returns bit 0: ray A survives, bit 1: ray B survives.
+__device__ __forceinline__ uint32_t tri_filter_sweep(const TriFlt &r, const float m, const RayPair &p) {
+	// det = d . n',  -t = d . (-m)   (negating every product negates the correctly rounded sum exactly)
+	const float2 det = __ffma2_rn(p.dz, bc(r.c.x), __ffma2_rn(p.dy, bc(r.b.x), __fmul2_rn(p.dx, bc(r.a.x))));
+	const float2 nt = __ffma2_rn(p.dz, bc(-r.c.y), __ffma2_rn(p.dy, bc(-r.b.y), __fmul2_rn(p.dx, bc(-r.a.y))));
+	const float2 su = __ffma2_rn(bc(r.f.x), p.cz, __ffma2_rn(bc(r.e.y), p.cy, __ffma2_rn(bc(r.e.x), p.cx, nt)));
 	// x = su sign(det) in [-M, |det| (1 + 2e-6) + M]  <=>  |su - det k| <= |det| k + M  with k = (1 + 2e-6) / 2: the
 	// interval test as a distance from its centre.  Same decision up to a few u |det| of rounding in the centre and
-	// half-width, which the slack in k and M absorbs; centre and half-width are one FFMA each (the filter
+	// half-width, which the slack in k and M absorbs; centre and half-width are one FMA each (the filter
 	// is not render.cl arithmetic, so nothing forbids fusing: one rounding instead of two only tightens the bound).
 	// A NaN fails `>` and survives.
-	const float diff = fma_(-det, 0.500001f, su);
-	const float w = fma_(fabsf(det), 0.500001f, m);
-	return !(fabsf(diff) > w);
+	const float2 diff = __ffma2_rn(make_float2(-det.x, -det.y), bc(0.500001f), su);
+	const float2 w = __ffma2_rn(make_float2(fabsf(det.x), fabsf(det.y)), bc(0.500001f), bc(m));
+	return (fabsf(diff.x) > w.x ? 0u : 1u) | (fabsf(diff.y) > w.y ? 0u : 2u);
 }
 // Two-strip filter for models with few, large triangles.  The u strip alone lets through every ray that crosses the
 // infinite band between the triangle's edge e2 and its parallel through v1 -- on a ~1k-triangle mesh about 18 pairs for
@@ -256,19 +236,18 @@ __device__ __forceinline__ bool tri_filter_sweep(const TriFlt &r, const float m,
 struct TriUV {
 	float4 q0, q1, q2, q3;
 };
-__device__ __forceinline__ bool tri_filter_sweep_uv(const TriUV &r, const float m, const float4 r0, const float4 r1,
-                                                    const float4 r2) {
-	const float det = fma_(r1.x, r.q0.z, fma_(r0.z, r.q0.y, r0.x * r.q0.x));
-	const float2 nt = __ffma2_rn(make_float2(r1.x, r1.y), make_float2(r.q2.x, r.q2.y),
-	                             __ffma2_rn(make_float2(r0.z, r0.w), make_float2(r.q1.z, r.q1.w),
-	                                        __fmul2_rn(make_float2(r0.x, r0.y), make_float2(r.q1.x, r.q1.y))));
-	const float2 ss = __ffma2_rn(make_float2(r2.z, r2.w), make_float2(r.q3.z, r.q3.w),
-	                             __ffma2_rn(make_float2(r2.x, r2.y), make_float2(r.q3.x, r.q3.y),
-	                                        __ffma2_rn(make_float2(r1.z, r1.w), make_float2(r.q2.z, r.q2.w), nt)));
-	const float du = fma_(-det, 0.500001f, ss.x);  // u det - det k
-	const float dv = fma_(det, 0.500001f, ss.y);   // -(v det - det k)
-	const float w = fma_(fabsf(det), 0.500001f, m);
-	return !(fabsf(du) > w) && !(fabsf(dv) > w);  // NaNs fail `>` and survive
+__device__ __forceinline__ uint32_t tri_filter_sweep_uv(const TriUV &r, const float m, const RayPair &p) {
+	// two rays per operation, like tri_filter_sweep; per half the operations and their order are the scalar filter's
+	const float2 det = __ffma2_rn(p.dz, bc(r.q0.z), __ffma2_rn(p.dy, bc(r.q0.y), __fmul2_rn(p.dx, bc(r.q0.x))));
+	const float2 nt = __ffma2_rn(p.dz, bc(r.q2.x), __ffma2_rn(p.dy, bc(r.q1.z), __fmul2_rn(p.dx, bc(r.q1.x))));   // d . (-m)
+	const float2 nt1 = __ffma2_rn(p.dz, bc(r.q2.y), __ffma2_rn(p.dy, bc(r.q1.w), __fmul2_rn(p.dx, bc(r.q1.y))));  // d . (-m1)
+	const float2 su = __ffma2_rn(p.cz, bc(r.q3.z), __ffma2_rn(p.cy, bc(r.q3.x), __ffma2_rn(p.cx, bc(r.q2.z), nt)));   // c . e2 - t
+	const float2 sv = __ffma2_rn(p.cz, bc(r.q3.w), __ffma2_rn(p.cy, bc(r.q3.y), __ffma2_rn(p.cx, bc(r.q2.w), nt1)));  // c . e1 - t1
+	const float2 du = __ffma2_rn(make_float2(-det.x, -det.y), bc(0.500001f), su);  // u det - det k
+	const float2 dv = __ffma2_rn(det, bc(0.500001f), sv);                          // -(v det - det k)
+	const float2 w = __ffma2_rn(make_float2(fabsf(det.x), fabsf(det.y)), bc(0.500001f), bc(m));
+	// NaNs fail `>` and survive
+	return ((fabsf(du.x) > w.x || fabsf(dv.x) > w.x) ? 0u : 1u) | ((fabsf(du.y) > w.y || fabsf(dv.y) > w.y) ? 0u : 2u);
 }
 __device__ __forceinline__ void test_triangle(const float4 v0, const float4 e1, const float4 e2, vec3 o, vec3 d,
                                               int shape, int tri, Hit &hit) {
@@ -545,27 +524,13 @@ __device__ __forceinline__ void camera_ray(const RenderParams &p, int gx, int gy
 }
 
 // Scatter at a hit, render.cl:418-462.  Updates o, d, mask; consumes 9 or 10 random numbers.
-// ROLLED: the three normal draws as a rolled loop (one copy of the code instead of three)
-template <bool ROLLED = false>
 __device__ __forceinline__ void scatter(const DevScene &sc, int material, vec3 pos, vec3 n, bool front,
                                         uint32_t &seed, vec3 &o, vec3 &d, vec3 &mask, float4 m0, float4 m1) {
 	o = pos;
 	// random_direction_hemisphere, :156-163
-	float gx = 0.f, gy = 0.f, gz = 0.f;
-	if (ROLLED) {
-		// three draws, ONE copy of the code: in the fused-frame builds the kernel's hot instructions (this loop plus the
-		// in-kernel resolve) would otherwise outgrow the 32 KB L1.5 instruction cache (stalled_no_instruction 0.6 -> 2.2
-		// per issue); the plain builds fit and keep the three inlined copies (1 % faster there)
-#pragma unroll 1
-		for (int k = 0; k < 3; ++k) {
-			gx = gy, gy = gz;
-			gz = random_float_normal(seed);
-		}
-	} else {
-		const float2 g = random_float_normal_x2(seed);  // two draws as packed FP32x2 chains: fewer issue slots
-		gx = g.x, gy = g.y;
-		gz = random_float_normal(seed);
-	}
+	const float2 g = random_float_normal_x2(seed);  // two draws as packed FP32x2 chains: fewer issue slots
+	const float gx = g.x, gy = g.y;
+	const float gz = random_float_normal(seed);
 	vec3 rd = normalize(mk(gx, gy, gz));
 	const float2 nn = dot_x2(n, rd, d);                         // {dot(n, rd), dot(n, d)}: one packed chain
 	rd = rd * sign_(nn.x);
@@ -662,7 +627,7 @@ constexpr int UV_MAX_TRIS = SRT_UV_MAX_TRIS;
 static_assert(TRIS_PER_LANE_UV <= TRIS_PER_LANE, "the survivor masks are sized for TRIS_PER_LANE slots");
 constexpr int TILE_BYTES = TILE_TRIS * FLT_BYTES > TILE_TRIS_UV * UV_BYTES ? TILE_TRIS * FLT_BYTES : TILE_TRIS_UV * UV_BYTES;
 constexpr int RING_BYTES = TILE_STAGES * TILE_BYTES;
-constexpr int RAYS_BYTES = 32 * 64;           // 32 rays x 4 float4: the filter's operands (3) and the origin for the exact test
+constexpr int RAYS_BYTES = 32 * 64;           // 32 rays x {origin, direction} (exact test) + 16 ray pairs x 12 floats (the filter)
 constexpr int PAIR_SLOTS = 256;               // ring of filter survivors (ray << 27 | triangle) awaiting the exact test
 constexpr int PAIRS_BYTES = PAIR_SLOTS * 4;
 constexpr int BEST_BYTES = 32 * 8;            // per parked ray: (t bits << 32 | triangle + 1), minimised atomically
@@ -746,16 +711,20 @@ __device__ SRT_PHASE_ATTR void triangle_phase(const DevScene &sc, int n, int tri
 	const int nrays = __popc(ray_mask);
 	const int slot = __popc(ray_mask & ((1u << lane) - 1u));
 	const uint32_t ray_bits = nrays >= 32 ? 0xffffffffu : (1u << nrays) - 1u;
-	if (active) {  // per-ray operands (64 B): d twice for the packed chains, c = o x d; the origin for the exact test
+	// the filter's operands, two rays to a record: 12 floats {A, B} x (d.x, d.y, d.z, c.x, c.y, c.z), c = o x d, for the
+	// rays in slots 2k and 2k + 1; and per ray its origin and direction for the exact test
+	float *pairbuf = reinterpret_cast<float *>(rays + 64);  // behind the 32 x 2 float4 of origins and directions
+	if (active) {
 		const vec3 c = cross(o, d);
-		rays[4 * slot] = make_float4(d.x, d.x, d.y, d.y);
-		rays[4 * slot + 1] = uv ? make_float4(d.z, d.z, c.x, c.x) : make_float4(d.z, d.z, c.x, c.y);
-		rays[4 * slot + 2] = uv ? make_float4(c.y, c.y, c.z, c.z) : make_float4(c.z, 0.f, 0.f, 0.f);
-		rays[4 * slot + 3] = make_float4(o.x, o.y, o.z, 0.f);
+		float *pr = pairbuf + 12 * (slot >> 1) + (slot & 1);
+		pr[0] = d.x, pr[2] = d.y, pr[4] = d.z, pr[6] = c.x, pr[8] = c.y, pr[10] = c.z;
+		rays[2 * slot] = make_float4(o.x, o.y, o.z, 0.f);
+		rays[2 * slot + 1] = make_float4(d.x, d.y, d.z, 0.f);
 		best[slot] = (unsigned long long)__float_as_uint(hit.t) << 32;
 	}
 	if ((nrays & 1) && lane == 0) {  // pad to an even count: a null ray (its survivor bits are masked off)
-		rays[4 * nrays] = rays[4 * nrays + 1] = rays[4 * nrays + 2] = rays[4 * nrays + 3] = make_float4(0.f, 0.f, 0.f, 0.f);
+		float *pr = pairbuf + 12 * (nrays >> 1) + 1;
+		pr[0] = pr[2] = pr[4] = pr[6] = pr[8] = pr[10] = 0.f;
 	}
 	int pair_head = 0, pair_count = 0;  // warp-uniform
 	// R = |o|_1 + K of my ray; its maximum over the parked rays (NaN -- a ray the filter cannot decide -- must win)
@@ -796,17 +765,14 @@ __device__ SRT_PHASE_ATTR void triangle_phase(const DevScene &sc, int n, int tri
 				// two parked rays per trip (the slots are dense: an odd count is padded with a null ray whose bit is masked
 				// off below).  A lane keeps, per triangle slot, the bit mask of the RAYS its triangle survived: one
 				// predicated OR per pair -- no vote, no hand-off to an owner lane.
-				const float4 *rp = rays;
-				uint32_t bit = 1u;
-				for (int i = 0; i < nrays; i += 2, rp += 8, bit <<= 2) {  // warp-uniform
-					const float4 a0 = rp[0], a1 = rp[1], b0 = rp[4], b1 = rp[5];
-					const float acz = reinterpret_cast<const float *>(rp + 2)[0];
-					const float bcz = reinterpret_cast<const float *>(rp + 6)[0];
+				const float4 *rp = reinterpret_cast<const float4 *>(pairbuf);
+				int sh = 0;
+				for (int i = 0; i < nrays; i += 2, rp += 3, sh += 2) {  // warp-uniform
+					const float4 p0 = rp[0], p1 = rp[1], p2 = rp[2];
+					const RayPair pr = {make_float2(p0.x, p0.y), make_float2(p0.z, p0.w), make_float2(p1.x, p1.y),
+					                    make_float2(p1.z, p1.w), make_float2(p2.x, p2.y), make_float2(p2.z, p2.w)};
 #pragma unroll
-					for (int q = 0; q < TRIS_PER_LANE; ++q) {
-						if (tri_filter_sweep(tf[q], tf[q].f.y, a0, a1, acz, q < SRT_PACKED_SLOTS)) cand[q] |= bit;
-						if (tri_filter_sweep(tf[q], tf[q].f.y, b0, b1, bcz, q < SRT_PACKED_SLOTS)) cand[q] |= bit << 1;
-					}
+					for (int q = 0; q < TRIS_PER_LANE; ++q) cand[q] |= tri_filter_sweep(tf[q], tf[q].f.y, pr) << sh;
 				}
 			} else {
 				// the same sweep with the two-strip filter: 80-byte records, TRIS_PER_LANE_UV triangles per lane
@@ -819,15 +785,14 @@ __device__ SRT_PHASE_ATTR void triangle_phase(const DevScene &sc, int n, int tri
 				}
 				__syncwarp();
 				if (lane == 0 && t + TILE_STAGES < ntiles) issue(t + TILE_STAGES);
-				const float4 *rp = rays;
-				uint32_t bit = 1u;
-				for (int i = 0; i < nrays; i += 2, rp += 8, bit <<= 2) {  // warp-uniform
-					const float4 a0 = rp[0], a1 = rp[1], a2 = rp[2], b0 = rp[4], b1 = rp[5], b2 = rp[6];
+				const float4 *rp = reinterpret_cast<const float4 *>(pairbuf);
+				int sh = 0;
+				for (int i = 0; i < nrays; i += 2, rp += 3, sh += 2) {  // warp-uniform
+					const float4 p0 = rp[0], p1 = rp[1], p2 = rp[2];
+					const RayPair pr = {make_float2(p0.x, p0.y), make_float2(p0.z, p0.w), make_float2(p1.x, p1.y),
+					                    make_float2(p1.z, p1.w), make_float2(p2.x, p2.y), make_float2(p2.z, p2.w)};
 #pragma unroll
-					for (int q = 0; q < TRIS_PER_LANE_UV; ++q) {
-						if (tri_filter_sweep_uv(tv[q], tv[q].q0.w, a0, a1, a2)) cand[q] |= bit;
-						if (tri_filter_sweep_uv(tv[q], tv[q].q0.w, b0, b1, b2)) cand[q] |= bit << 1;
-					}
+					for (int q = 0; q < TRIS_PER_LANE_UV; ++q) cand[q] |= tri_filter_sweep_uv(tv[q], tv[q].q0.w, pr) << sh;
 				}
 			}
 			// the padding ray's bit, and triangles beyond the end of the list (the tile holds stale shared memory there)
@@ -875,9 +840,8 @@ __device__ SRT_PHASE_ATTR void triangle_phase(const DevScene &sc, int n, int tri
 					const uint32_t pr = pairs[(pair_head + lane) & (PAIR_SLOTS - 1)];
 					const int r = pr >> 27, j = pr & (MAX_SWEEP_TRIS - 1);
 					SRT_ASSERT(j >= 0 && j < n && r < nrays);
-					const float4 q0 = rays[4 * r], q1 = rays[4 * r + 1], q3 = rays[4 * r + 3];
-					exact_pair(__ldg(exact + 3 * (size_t)j), __ldg(exact + 3 * (size_t)j + 1), __ldg(exact + 3 * (size_t)j + 2), q3,
-					           make_float4(q0.x, q0.z, q1.x, 0.f), best + r, j);
+					exact_pair(__ldg(exact + 3 * (size_t)j), __ldg(exact + 3 * (size_t)j + 1), __ldg(exact + 3 * (size_t)j + 2),
+					           rays[2 * r], rays[2 * r + 1], best + r, j);
 				}
 				pair_head = (pair_head + m) & (PAIR_SLOTS - 1);
 				pair_count -= m;
@@ -917,102 +881,6 @@ __device__ __forceinline__ uchar4 argb_pixel(float4 c, float steps) {
 	// uchar4(255, r, g, b): A,R,G,B byte order, float -> uchar by truncation
 	return make_uchar4(255, (unsigned char)(int)r, (unsigned char)(int)g, (unsigned char)(int)b);
 }
-// the same with ONE copy of the per-channel code (a rolled loop that rotates the channels through): for the fused frame,
-// where this sits inside the render kernel and instruction-cache footprint matters more than a few loop instructions
-__device__ __forceinline__ uchar4 argb_pixel_rolled(float4 c, float steps) {
-	float r = c.x, g = c.y, b = c.z;
-#pragma unroll 1
-	for (int k = 0; k < 3; ++k) {
-		const float v = aces_sqrt(div_(r, steps)) * 255.0f;
-		r = g, g = b, b = v;
-	}
-	return make_uchar4(255, (unsigned char)(int)r, (unsigned char)(int)g, (unsigned char)(int)b);
-}
-
-// ---- fused frame: per-warp ring of completed pixels (FrameOut) -----------------------------------------------------
-__device__ __forceinline__ void fence_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
-constexpr int PIXQ_SLOTS = 64;  // < 32 left over + <= 32 pushed at a time
-constexpr int PIXQ_BYTES = PIXQ_SLOTS * 4;
-struct PixRing {
-	uint32_t *q;
-	int head, count;  // warp-uniform
-};
-// Resolve n <= 32 queued pixels, one per lane: color = sum of the pixel's samples in sample order (render.cl:494-519),
-// color /= num_samples (:520), canvas[id] += color (:522) -- accumulate_kernel's arithmetic -- then kernel `average`
-// for that pixel; count the pixel towards its row, the row towards its band, and publish a completed band to the host.
-__device__ __noinline__ void flush_pixels(const RenderParams &p, const FrameOut &fo, const float4 *scratch, PixRing &ring,
-                                             int n, int lane) {
-	fence_gpu();  // the samples below were written by other threads (published through pix_done)
-	int row = -1;
-	if (lane < n) {
-		const unsigned int pix = ring.q[(ring.head + lane) & (PIXQ_SLOTS - 1)];  // full frame: local pixel == pixel id
-		float4 c = __ldcg(&fo.canvas[pix]);
-		const float4 *s = scratch + (size_t)pix * p.num_samples;
-		vec3 color = mk(0, 0, 0);
-		for (int k = 0; k < p.num_samples; ++k) color = color + xyz(__ldcg(&s[k]));
-		if (p.inv_ns != 0.0f) {  // x / 2^k == x * 2^-k exactly
-			c.x += color.x * p.inv_ns, c.y += color.y * p.inv_ns, c.z += color.z * p.inv_ns;
-		} else {
-			const float ns_f = (float)p.num_samples;
-			c.x += div_(color.x, ns_f), c.y += div_(color.y, ns_f), c.z += div_(color.z, ns_f);
-		}
-		fo.canvas[pix] = c;
-		fo.output[pix] = argb_pixel_rolled(c, (float)fo.num_steps);
-		row = (int)(pix / (unsigned)p.width);
-		fence_gpu();  // my pixel before the row counter
-	}
-	ring.head = (ring.head + n) & (PIXQ_SLOTS - 1);
-	ring.count -= n;
-	__syncwarp();
-	if (lane < n) {
-		const unsigned act = n >= 32 ? 0xffffffffu : (1u << n) - 1u;
-		const unsigned same = __match_any_sync(act, row);
-		if (lane == __ffs(same) - 1) {  // one atomic per row per flush
-			const unsigned int k = (unsigned)__popc(same);
-			if (atomicAdd(&fo.row_done[row], k) + k == (unsigned)p.width) {
-				fo.row_done[row] = 0;
-				const int band = row / fo.band_rows;
-				const int rows_in_band = min(fo.band_rows, p.height - band * fo.band_rows);
-				fence_gpu();
-				if (atomicAdd(&fo.band_done[band], 1u) + 1u == (unsigned)rows_in_band) {
-					fo.band_done[band] = 0;
-					__threadfence_system();  // the band's ARGB8 pixels before the flag the host (and then a copy engine) acts on
-					fo.host_flags[band] = fo.epoch;
-				}
-			}
-		}
-	}
-	__syncwarp();
-}
-// Every lane of the warp calls this once per site where samples can finish; `fin`: my sample `item` just finished and
-// its radiance is in scratch[item].
-template <bool FUSE>
-__device__ __forceinline__ void sample_done(const RenderParams &p, const FrameOut &fo, const float4 *scratch, PixRing &ring,
-                                            bool fin, unsigned int item, int lane) {
-	if (!FUSE) return;
-	unsigned int lp = 0;
-	bool complete = false;
-	if (fin) {
-		lp = fo.ns_shift >= 0 ? item >> fo.ns_shift : item / (unsigned)p.num_samples;
-		if (p.num_samples == 1) {
-			complete = true;
-		} else {
-			// my sample before the counter: a RELEASE increment (one MEMBAR, and -- unlike a fence -- no L1 invalidation)
-			unsigned int old;
-			asm volatile("atom.add.release.gpu.global.u32 %0, [%1], 1;" : "=r"(old) : "l"(fo.pix_done + lp) : "memory");
-			complete = old == (unsigned)p.num_samples - 1u;
-			if (complete) fo.pix_done[lp] = 0;  // nobody touches this pixel again before the next launch
-		}
-	}
-	const unsigned cm = __ballot_sync(0xffffffffu, complete);
-	if (cm) {
-		if (complete) ring.q[(ring.head + ring.count + __popc(cm & ((1u << lane) - 1u))) & (PIXQ_SLOTS - 1)] = lp;
-		ring.count += __popc(cm);
-		__syncwarp();
-		if (ring.count >= 32) flush_pixels(p, fo, scratch, ring, 32, lane);
-	}
-}
-
 // Start the camera path of work item `item` = local_pixel * num_samples + sample (render.cl:488-516).
 __device__ __forceinline__ void start_path(const RenderParams &p, unsigned int item, uint32_t &seed, vec3 &o, vec3 &d) {
 	const unsigned int launch = p.num_launches > 1 ? item / p.items_per_launch : 0u;
@@ -1072,11 +940,10 @@ enum { MODE_ANALYTIC = 0, MODE_SMALL_MODELS = 1, MODE_BIG_MODELS = 2, MODE_BVH =
 // the camera rays did through their rings, and hit shading -- the bulk of the instructions -- no longer runs with only
 // the ~25 lanes whose ray happened to hit something in that trip.  Every path executes exactly the operations it
 // executed before, in the same order; only which lane executes them changes.
-template <bool COUNT, int MODE, bool FUSE>
+template <bool COUNT, int MODE>
 __device__ __forceinline__ void render_wavefront(const RenderParams &p, const DevScene &sc, const ShapeTable &tab,
-                                                 const FrameOut &fo, float4 *__restrict__ scratch,
-                                                 unsigned long long *__restrict__ cursor, Counters &cnt,
-                                                 unsigned char *smem_raw) {
+                                                 float4 *__restrict__ scratch, unsigned long long *__restrict__ cursor,
+                                                 Counters &cnt, unsigned char *smem_raw) {
 	const unsigned FULL = 0xffffffffu;
 	constexpr bool MODELS = MODE != MODE_ANALYTIC && MODE != MODE_ANALYTIC_CONST;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1087,11 +954,6 @@ __device__ __forceinline__ void render_wavefront(const RenderParams &p, const De
 	int ray_head = 0, ray_count = 0, sky_head = 0, sky_count = 0, hit_head = 0, hit_count = 0;  // warp-uniform
 	bool exhausted = false;
 	const vec3 cam_origin = mk(p.c2w[12], p.c2w[13], p.c2w[14]);
-	// fused frame: the ring of completed pixels takes the hit record's triangle word, which scenes without models
-	// do not use; the builds that know models get PIXQ_BYTES more per warp behind the queues
-	PixRing pixq = {MODELS ? reinterpret_cast<uint32_t *>(smem_raw + QUEUE_SMEM_BYTES + warp * PIXQ_BYTES)
-	                       : hitq + (HITQ_WORDS - 1) * QUEUE_SLOTS, 0, 0};
-
 	auto flush_sky = [&](int n) {  // mask *= sky, color += mask (:464-465) for n <= 32 queued records, one per lane
 		unsigned int it = 0;
 		if (lane < n) {
@@ -1101,20 +963,16 @@ __device__ __forceinline__ void render_wavefront(const RenderParams &p, const De
 			vec3 m = mk(skyq[4 * QUEUE_SLOTS + sl], skyq[5 * QUEUE_SLOTS + sl], skyq[6 * QUEUE_SLOTS + sl]);
 			const vec3 dir = mk(skyq[7 * QUEUE_SLOTS + sl], skyq[8 * QUEUE_SLOTS + sl], skyq[9 * QUEUE_SLOTS + sl]);
 			m = m * sky_box(sc, dir);
-			// fused frame: a path that ended at a hit travels through this ring as well (marked by d.x = 2, which no
-			// direction -- always the output of normalize(): at most 1 + a few ulp, or 0 / inf / NaN -- can be)
-			const vec3 r = (FUSE && dir.x == 2.0f) ? c : c + m;
+			const vec3 r = c + m;
 			scratch[it] = make_float4(r.x, r.y, r.z, 0.f);
 		}
 		sky_head = (sky_head + n) & (QUEUE_SLOTS - 1);
 		sky_count -= n;
 		__syncwarp();
-		sample_done<FUSE>(p, fo, scratch, pixq, lane < n, it, lane);
 	};
 
 	for (;;) {
 		bool has_ray = false;
-		bool fin = false;  // fused frame: my path ended at a hit in this trip; its radiance goes out through the sky ring
 		unsigned int item = 0;
 		int bounce = 0;
 		uint32_t seed = 0;
@@ -1156,18 +1014,13 @@ __device__ __forceinline__ void render_wavefront(const RenderParams &p, const De
 						done = true;
 					} else {
 						const float4 m1 = __ldg(&sc.materials[4 * material + 1]);
-						scatter<FUSE>(sc, material, pos, n_, front, seed, o, d, mask, m0, m1);
+						scatter(sc, material, pos, n_, front, seed, o, d, mask, m0, m1);
 						bounce += 1;
 						done = false;
 					}
 				}
-				// the sample's radiance, summed per pixel in sample order later.  Fused frame: every finished sample
-				// leaves through the sky ring (ONE site that counts completed samples, with all lanes active): the lane
-				// sits out this trip's scan and pushes {item, radiance} with the escaped paths, marked d.x = 2 (see
-				// flush_sky).  (Keeping such a lane in the scan as a pseudo-ray measured 4 % slower.)
-				if (done && !FUSE) scratch[item] = make_float4(color.x, color.y, color.z, 0.f);
-				if (!done) has_ray = true;
-				fin = FUSE && done;
+				if (done) scratch[item] = make_float4(color.x, color.y, color.z, 0.f);  // summed per pixel in sample order later
+				else has_ray = true;
 			}
 			hit_head = (hit_head + n) & (QUEUE_SLOTS - 1);
 			hit_count -= n;
@@ -1175,7 +1028,7 @@ __device__ __forceinline__ void render_wavefront(const RenderParams &p, const De
 		}
 
 		// -- 2. the other lanes take fresh camera rays (start_path, 32 at a time with every lane active)
-		const unsigned need = __ballot_sync(FULL, !has_ray && !fin);
+		const unsigned need = __ballot_sync(FULL, !has_ray);
 		if (need) {
 			const int want = __popc(need);
 			if (ray_count < want && !exhausted) {
@@ -1204,7 +1057,7 @@ __device__ __forceinline__ void render_wavefront(const RenderParams &p, const De
 				exhausted = vm != FULL;
 				__syncwarp();
 			}
-			if (!has_ray && !fin) {
+			if (!has_ray) {
 				const int r = __popc(need & lt_mask);
 				if (r < ray_count) {
 					const int sl = (ray_head + r) & (QUEUE_SLOTS - 1);
@@ -1224,7 +1077,7 @@ __device__ __forceinline__ void render_wavefront(const RenderParams &p, const De
 			ray_count -= popped;
 			__syncwarp();
 		}
-		const bool any_ray = __any_sync(FULL, has_ray || fin);
+		const bool any_ray = __any_sync(FULL, has_ray);
 		if (!any_ray && hit_count > 0) continue;  // only queued hits are left: the next trip shades them
 		// !any_ray: nothing in flight, the frame is done for this warp once the sky ring is empty (ONE flush site below:
 		// the sky box is the largest block of code in the kernel, and a second inlined copy costs instruction cache)
@@ -1239,7 +1092,7 @@ __device__ __forceinline__ void render_wavefront(const RenderParams &p, const De
 
 		// -- 4. hits -> hit ring (position = origin + direction * t, :311 / :337 / :361); escaped paths -> sky ring
 		const bool is_hit = has_ray && hit.shape >= 0, is_miss = has_ray && hit.shape < 0;
-		const unsigned hm = __ballot_sync(FULL, is_hit), sm = __ballot_sync(FULL, is_miss || fin);
+		const unsigned hm = __ballot_sync(FULL, is_hit), sm = __ballot_sync(FULL, is_miss);
 		if (is_hit) {
 			const vec3 pos = cfma3(d, hit.t, o);
 			const int sl = (hit_head + hit_count + __popc(hm & lt_mask)) & (QUEUE_SLOTS - 1);
@@ -1256,13 +1109,13 @@ __device__ __forceinline__ void render_wavefront(const RenderParams &p, const De
 			hitq[14 * QUEUE_SLOTS + sl] = ((uint32_t)hit.shape << 8) | (uint32_t)bounce;
 			if (MODELS) hitq[15 * QUEUE_SLOTS + sl] = (uint32_t)hit.tri;
 		}
-		if (is_miss || fin) {
+		if (is_miss) {
 			if (COUNT) cnt.sky += 1;
 			const int sl = (sky_head + sky_count + __popc(sm & lt_mask)) & (QUEUE_SLOTS - 1);
 			skyq[0 * QUEUE_SLOTS + sl] = __uint_as_float(item);
 			skyq[1 * QUEUE_SLOTS + sl] = color.x, skyq[2 * QUEUE_SLOTS + sl] = color.y, skyq[3 * QUEUE_SLOTS + sl] = color.z;
 			skyq[4 * QUEUE_SLOTS + sl] = mask.x, skyq[5 * QUEUE_SLOTS + sl] = mask.y, skyq[6 * QUEUE_SLOTS + sl] = mask.z;
-			skyq[7 * QUEUE_SLOTS + sl] = fin ? 2.0f : d.x, skyq[8 * QUEUE_SLOTS + sl] = d.y, skyq[9 * QUEUE_SLOTS + sl] = d.z;
+			skyq[7 * QUEUE_SLOTS + sl] = d.x, skyq[8 * QUEUE_SLOTS + sl] = d.y, skyq[9 * QUEUE_SLOTS + sl] = d.z;
 		}
 		hit_count += __popc(hm);
 		sky_count += __popc(sm);
@@ -1270,17 +1123,16 @@ __device__ __forceinline__ void render_wavefront(const RenderParams &p, const De
 		if (sky_count >= 32 || (!any_ray && sky_count > 0)) flush_sky(min(sky_count, 32));  // (< 32 are left after a trip)
 		if (!any_ray) break;
 	}
-	if (FUSE && pixq.count > 0) flush_pixels(p, fo, scratch, pixq, pixq.count, lane);
 }
 
 // WF: the queue builds exist with both schedules -- wavefront (hits shaded 32 at a time through the hit ring) for
 // launches that keep every thread busy for many items, plain (hits shaded in place) for short ones, where queueing a
 // hit until 32 are there only lengthens the ragged end (BASELINE config 1, 3 items per thread: +6 % plain) and for
 // launches whose bounce count does not fit the hit record's 8 bits.
-template <bool COUNT, int MODE, bool WF, bool FUSE>
+template <bool COUNT, int MODE, bool WF>
 __global__ void __launch_bounds__(RENDER_THREADS, MODE == MODE_BIG_MODELS ? SRT_MIN_BLOCKS : (MODE == MODE_BVH ? SRT_MIN_BLOCKS_BVH : SRT_MIN_BLOCKS_ANALYTIC))
 render_kernel(const __grid_constant__ RenderParams p, const __grid_constant__ DevScene sc,
-              const __grid_constant__ ShapeTable tab, const __grid_constant__ FrameOut fo, float4 *__restrict__ scratch,
+              const __grid_constant__ ShapeTable tab, float4 *__restrict__ scratch,
               unsigned long long *__restrict__ cursor, Counters *__restrict__ counters) {
 	const unsigned FULL = 0xffffffffu;
 	const int lane = threadIdx.x & 31;
@@ -1293,7 +1145,7 @@ render_kernel(const __grid_constant__ RenderParams p, const __grid_constant__ De
 	// per-warp ring of triangle tiles + one mbarrier per stage
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	if (QUEUES && WF) {  // the wavefront schedule (the loop below is the plain schedule and the dense-sweep build)
-		render_wavefront<COUNT, MODE, FUSE>(p, sc, tab, fo, scratch, cursor, cnt, smem_raw);
+		render_wavefront<COUNT, MODE>(p, sc, tab, scratch, cursor, cnt, smem_raw);
 		if (COUNT) {
 			unsigned long long *c = reinterpret_cast<unsigned long long *>(&cnt);
 			for (int k = 0; k < 6; ++k) {
@@ -1338,12 +1190,6 @@ render_kernel(const __grid_constant__ RenderParams p, const __grid_constant__ De
 	bool exhausted = false;
 	const unsigned lt_mask = (1u << lane) - 1u;
 	const vec3 cam_origin = mk(p.c2w[12], p.c2w[13], p.c2w[14]);
-	// fused frame: ring of completed pixels -- in the (unused) hit-ring space of the plain queue builds, behind the
-	// sweep's shared memory in the dense-sweep build
-	PixRing pixq = {PHASES ? reinterpret_cast<uint32_t *>(smem_raw + RENDER_SMEM_BYTES + BIG_SKYQ_BYTES + warp * PIXQ_BYTES)
-	                       : (SRT_WAVEFRONT ? rayq + (RAYQ_WORDS + SKYQ_WORDS) * QUEUE_SLOTS
-	                                        : reinterpret_cast<uint32_t *>(smem_raw + QUEUE_SMEM_BYTES + warp * PIXQ_BYTES)), 0, 0};
-
 	// evaluate `n` queued sky records (n <= 32), one per lane: mask *= sky, color += mask (:464-465)
 	auto flush_sky = [&](int n) {
 		unsigned int it = 0;
@@ -1360,7 +1206,6 @@ render_kernel(const __grid_constant__ RenderParams p, const __grid_constant__ De
 		sky_head = (sky_head + n) & (QUEUE_SLOTS - 1);
 		sky_count -= n;
 		__syncwarp();
-		sample_done<FUSE>(p, fo, scratch, pixq, lane < n, it, lane);
 	};
 
 	for (;;) {
@@ -1447,8 +1292,6 @@ render_kernel(const __grid_constant__ RenderParams p, const __grid_constant__ De
 		const bool any_alive = __any_sync(FULL, alive);
 
 		bool push_sky = false;
-		bool fin = false;            // my sample finished in this trip (fused frame)
-		unsigned int fin_item = 0;
 		if (alive && park < 0 && !ready) {
 			if (scan_at < 0) {  // new bounce: closest_intersection prologue, :294-297
 				if (COUNT) cnt.bounces += 1;
@@ -1497,7 +1340,7 @@ render_kernel(const __grid_constant__ RenderParams p, const __grid_constant__ De
 							done = true;
 						} else {
 							const float4 m1 = __ldg(&sc.materials[4 * material + 1]);
-							scatter<FUSE>(sc, material, pos, n, front, seed, o, d, mask, m0, m1);
+							scatter(sc, material, pos, n, front, seed, o, d, mask, m0, m1);
 							bounce += 1;
 							done = false;
 						}
@@ -1517,11 +1360,9 @@ render_kernel(const __grid_constant__ RenderParams p, const __grid_constant__ De
 				if (done) {  // the sample's radiance; accumulate_kernel sums a pixel's samples in order (:518-522)
 					scratch[item] = make_float4(color.x, color.y, color.z, 0.f);
 					fresh = true;
-					fin = true, fin_item = item;
 				}
 			}
 		}
-		if (FUSE && __any_sync(FULL, fin)) sample_done<FUSE>(p, fo, scratch, pixq, fin, fin_item, lane);
 
 		if (SKYQ) {  // escaped paths: queue {item, color, mask, direction}; evaluate the sky box 32 at a time
 			const unsigned sm = __ballot_sync(FULL, push_sky);
@@ -1568,8 +1409,6 @@ render_kernel(const __grid_constant__ RenderParams p, const __grid_constant__ De
 			}
 		}
 	}
-
-	if (FUSE && pixq.count > 0) flush_pixels(p, fo, scratch, pixq, pixq.count, lane);
 
 	if (COUNT) {
 		unsigned long long *c = reinterpret_cast<unsigned long long *>(&cnt);

@@ -99,23 +99,14 @@ struct srt_tracer {
 	int band_h = 1, band_i = 0, band_n = 1;
 	int uv_max_tris = srt::UV_MAX_TRIS;  // srt_set_sweep_filter
 	int schedule = SRT_SCHEDULE_AUTO;    // srt_set_schedule
-	int render_grid[3][5][2] = {};  // [plain / counted / fused frame][mode][wavefront]
+	int render_grid[2][5][2] = {};  // [counted][mode][wavefront]
 	srt::ShapeTable shape_table{};  // the first CONST_SHAPES shape records, passed as a kernel parameter
 
-	// fused frame (srt_render_frame, srt::FrameOut): completion counters, the band flags the kernel publishes in
-	// host-mapped memory, and the second stream the bands' read-backs run on while the frame is still being traced
 	int frame_pipeline = SRT_FRAME_AUTO;  // srt_set_frame_pipeline
 	// set for the duration of one srt_render_frame into the pinned caller vector: the launch's epilogue is
 	// frame_epilogue_kernel (accumulate + average + store to the host) instead of accumulate_kernel
 	uchar4 *epilogue_host = nullptr;
 	uint32_t epilogue_steps = 0;
-	unsigned int *pix_done = nullptr, *row_done = nullptr, *band_done = nullptr;
-	unsigned int *host_flags = nullptr;
-	unsigned int frame_epoch = 0;
-	bool frame_counters_dirty = true;
-	cudaStream_t copy_stream = nullptr;
-	cudaEvent_t frame_ev = nullptr;
-	cudaEvent_t band_ev[srt::FRAME_MAX_BANDS] = {};
 
 	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing;  // kernel launches since last query
 	uint64_t timed_launches = 0;                               // reference launches they cover (batches count each)
@@ -215,35 +206,26 @@ int make_params(srt_tracer *t, const srt_render_data *rd, srt::RenderParams &p) 
 	return SRT_OK;
 }
 
-template <bool COUNT, int MODE, bool WF, bool FUSE>
-int launch_render_impl(srt_tracer *t, const srt::RenderParams &p, const srt::FrameOut *fo);
+template <bool COUNT, int MODE, bool WF>
+int launch_render_impl(srt_tracer *t, const srt::RenderParams &p);
 
 // The wavefront schedule queues a hit until 32 are there to shade: worth it once a launch keeps every thread busy for
 // many items (+1.6 % on BASELINE config 2), not for a launch of a few items per thread (config 1: -6 %).  Its hit record
 // keeps the bounce count in 8 bits and the shape index in 24; anything else runs the plain schedule.
-// fo: non-null for the fused frame of srt_render_frame (FUSE builds; never instrumented)
 template <bool COUNT, int MODE>
-int launch_render_impl(srt_tracer *t, const srt::RenderParams &p, const srt::FrameOut *fo) {
+int launch_render_impl(srt_tracer *t, const srt::RenderParams &p) {
 	const bool fits = p.num_bounces <= 256 && t->n_shapes < ((size_t)1 << 24);
 	const bool wf = SRT_WAVEFRONT && MODE != srt::MODE_BIG_MODELS && fits && t->schedule != SRT_SCHEDULE_PLAIN &&
 	                (p.total_items >= (4u << 20) || t->schedule == SRT_SCHEDULE_WAVEFRONT);
-	constexpr bool CAN_WF = MODE != srt::MODE_BIG_MODELS;
-	if (!COUNT && fo) {
-		if (CAN_WF && wf) return launch_render_impl<false, MODE, CAN_WF, true>(t, p, fo);
-		return launch_render_impl<false, MODE, false, true>(t, p, fo);
-	}
-	if (CAN_WF && wf) return launch_render_impl<COUNT, MODE, CAN_WF, false>(t, p, nullptr);
-	return launch_render_impl<COUNT, MODE, false, false>(t, p, nullptr);
+	if (MODE != srt::MODE_BIG_MODELS && wf) return launch_render_impl<COUNT, MODE, MODE != srt::MODE_BIG_MODELS>(t, p);
+	return launch_render_impl<COUNT, MODE, false>(t, p);
 }
 
-template <bool COUNT, int MODE, bool WF, bool FUSE>
-int launch_render_impl(srt_tracer *t, const srt::RenderParams &p, const srt::FrameOut *fo) {
-	auto kernel = srt::render_kernel<COUNT, MODE, WF, FUSE>;
-	constexpr bool MODELS = MODE != srt::MODE_ANALYTIC && MODE != srt::MODE_ANALYTIC_CONST;
-	// the fused frame's ring of completed pixels: see render_wavefront / render_kernel for where it lives
-	constexpr int pixq = !FUSE ? 0 : (MODE == srt::MODE_BIG_MODELS || (WF && MODELS) || !SRT_WAVEFRONT) ? srt::RENDER_WARPS * srt::PIXQ_BYTES : 0;
-	const int smem = (MODE == srt::MODE_BIG_MODELS ? srt::RENDER_SMEM_BYTES + srt::BIG_SKYQ_BYTES : srt::QUEUE_SMEM_BYTES) + pixq;
-	int &grid = t->render_grid[FUSE ? 2 : (COUNT ? 1 : 0)][MODE][WF ? 1 : 0];
+template <bool COUNT, int MODE, bool WF>
+int launch_render_impl(srt_tracer *t, const srt::RenderParams &p) {
+	auto kernel = srt::render_kernel<COUNT, MODE, WF>;
+	const int smem = MODE == srt::MODE_BIG_MODELS ? srt::RENDER_SMEM_BYTES + srt::BIG_SKYQ_BYTES : srt::QUEUE_SMEM_BYTES;
+	int &grid = t->render_grid[COUNT ? 1 : 0][MODE][WF ? 1 : 0];
 	if (grid == 0) {
 		int per_sm = 0;
 		if (smem) SRT_CUDA(t, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -262,12 +244,11 @@ int launch_render_impl(srt_tracer *t, const srt::RenderParams &p, const srt::Fra
 	}
 	const srt::DevScene sc = dev_scene(t);
 	cudaError_t le = cudaEventRecord(ev.first, t->stream);
-	kernel<<<grid, srt::RENDER_THREADS, smem, t->stream>>>(p, sc, t->shape_table, FUSE ? *fo : srt::FrameOut{}, t->scratch.ptr,
-	                                                        t->cursor, t->counters);
-	if (!FUSE && t->epilogue_host)
+	kernel<<<grid, srt::RENDER_THREADS, smem, t->stream>>>(p, sc, t->shape_table, t->scratch.ptr, t->cursor, t->counters);
+	if (t->epilogue_host)
 		srt::frame_epilogue_kernel<<<((p.total_pixels + 3) / 4 + 255) / 256, 256, 0, t->stream>>>(p, t->scratch.ptr, t->canvas, t->output,
 		                                                                                        t->epilogue_host, t->epilogue_steps);
-	else if (!FUSE)
+	else
 		srt::accumulate_kernel<<<(p.total_pixels + 255) / 256, 256, 0, t->stream>>>(p, t->scratch.ptr, t->canvas);
 	if (le == cudaSuccess) le = cudaEventRecord(ev.second, t->stream);
 	if (le == cudaSuccess) le = cudaGetLastError();
@@ -286,12 +267,12 @@ int launch_render_impl(srt_tracer *t, const srt::RenderParams &p, const srt::Fra
 }
 
 template <bool COUNT>
-int launch_params(srt_tracer *t, const srt::RenderParams &p, const srt::FrameOut *fo = nullptr) {
-	if (!t->has_models && t->n_shapes <= (size_t)srt::CONST_SHAPES) return launch_render_impl<COUNT, srt::MODE_ANALYTIC_CONST>(t, p, fo);
-	if (!t->has_models) return launch_render_impl<COUNT, srt::MODE_ANALYTIC>(t, p, fo);
-	if (t->accel == SRT_ACCEL_BVH && t->bvh_ready && t->has_big_models) return launch_render_impl<COUNT, srt::MODE_BVH>(t, p, fo);
-	if (!t->has_big_models) return launch_render_impl<COUNT, srt::MODE_SMALL_MODELS>(t, p, fo);
-	return launch_render_impl<COUNT, srt::MODE_BIG_MODELS>(t, p, fo);
+int launch_params(srt_tracer *t, const srt::RenderParams &p) {
+	if (!t->has_models && t->n_shapes <= (size_t)srt::CONST_SHAPES) return launch_render_impl<COUNT, srt::MODE_ANALYTIC_CONST>(t, p);
+	if (!t->has_models) return launch_render_impl<COUNT, srt::MODE_ANALYTIC>(t, p);
+	if (t->accel == SRT_ACCEL_BVH && t->bvh_ready && t->has_big_models) return launch_render_impl<COUNT, srt::MODE_BVH>(t, p);
+	if (!t->has_big_models) return launch_render_impl<COUNT, srt::MODE_SMALL_MODELS>(t, p);
+	return launch_render_impl<COUNT, srt::MODE_BIG_MODELS>(t, p);
 }
 
 template <bool COUNT>
@@ -416,12 +397,6 @@ int srt_destroy(srt_tracer *t) {
 	if (t->registered_out) cudaHostUnregister(t->registered_out);
 	for (auto &e : t->chunk_ev)
 		if (e) cudaEventDestroy(e);
-	if (t->copy_stream) cudaStreamSynchronize(t->copy_stream), cudaStreamDestroy(t->copy_stream);
-	if (t->frame_ev) cudaEventDestroy(t->frame_ev);
-	for (auto &e : t->band_ev)
-		if (e) cudaEventDestroy(e);
-	cudaFree(t->pix_done), cudaFree(t->row_done), cudaFree(t->band_done);
-	if (t->host_flags) cudaFreeHost(t->host_flags);
 	cudaGetLastError();
 	cudaFree(t->canvas);
 	cudaFree(t->output);
@@ -713,115 +688,19 @@ int srt_unpin_output(srt_tracer *t) {
 	return SRT_OK;
 }
 
-// Lazily created state of the fused frame.
-static int ensure_frame_state(srt_tracer *t) {
-	const size_t n = (size_t)t->width * t->height;
-	if (!t->copy_stream) SRT_CUDA(t, cudaStreamCreateWithFlags(&t->copy_stream, cudaStreamNonBlocking));
-	if (!t->frame_ev) SRT_CUDA(t, cudaEventCreateWithFlags(&t->frame_ev, cudaEventDisableTiming));
-	for (auto &e : t->band_ev)
-		if (!e) SRT_CUDA(t, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-	if (!t->pix_done) SRT_CUDA(t, cudaMalloc(&t->pix_done, n * sizeof(unsigned int)));
-	if (!t->row_done) SRT_CUDA(t, cudaMalloc(&t->row_done, (size_t)t->height * sizeof(unsigned int)));
-	if (!t->band_done) SRT_CUDA(t, cudaMalloc(&t->band_done, srt::FRAME_MAX_BANDS * sizeof(unsigned int)));
-	if (!t->host_flags) {
-		SRT_CUDA(t, cudaHostAlloc(&t->host_flags, srt::FRAME_MAX_BANDS * sizeof(unsigned int), cudaHostAllocMapped));
-		memset(t->host_flags, 0, srt::FRAME_MAX_BANDS * sizeof(unsigned int));
-	}
-	if (t->frame_counters_dirty) {  // first use, or a frame that did not run to completion
-		SRT_CUDA(t, cudaMemsetAsync(t->pix_done, 0, n * sizeof(unsigned int), t->stream));
-		SRT_CUDA(t, cudaMemsetAsync(t->row_done, 0, (size_t)t->height * sizeof(unsigned int), t->stream));
-		SRT_CUDA(t, cudaMemsetAsync(t->band_done, 0, srt::FRAME_MAX_BANDS * sizeof(unsigned int), t->stream));
-		t->frame_counters_dirty = false;
-	}
-	return SRT_OK;
-}
-
-// Tracer::render (src/tracer.cpp:103-116) as ONE pass: the kernel accumulates, resolves and publishes finished bands of
-// rows while it traces (srt::FrameOut), this thread -- which the reference blocks in enqueue_read_buffer anyway -- polls
-// the band flags and starts each band's copy the moment it is complete.
-static int render_frame_fused(srt_tracer *t, const srt::RenderParams &p, uint32_t ticks_stopped, uint8_t *argb_out) {
-	if (int rc = ensure_frame_state(t)) return rc;
-	const int band_rows = (t->height + srt::FRAME_MAX_BANDS / 2 - 1) / (srt::FRAME_MAX_BANDS / 2);  // <= 32 bands
-	const int n_bands = (t->height + band_rows - 1) / band_rows;
-	if (++t->frame_epoch == 0) t->frame_epoch = 1;
-	srt::FrameOut fo{};
-	fo.canvas = t->canvas;
-	fo.output = t->output;
-	fo.pix_done = t->pix_done, fo.row_done = t->row_done, fo.band_done = t->band_done;
-	unsigned int *dev_flags = nullptr;
-	SRT_CUDA(t, cudaHostGetDevicePointer((void **)&dev_flags, t->host_flags, 0));
-	fo.host_flags = dev_flags;
-	fo.epoch = t->frame_epoch;
-	fo.num_steps = ticks_stopped;
-	fo.band_rows = band_rows;
-	fo.ns_shift = -1;
-	for (int k = 0; k < 31; ++k)
-		if (p.num_samples == (1 << k)) fo.ns_shift = k;
-	t->frame_counters_dirty = true;  // until the frame has run to completion
-	if (int rc = launch_params<false>(t, p, &fo)) return rc;
-	SRT_CUDA(t, cudaEventRecord(t->frame_ev, t->stream));
-
-	const size_t row_bytes = (size_t)t->width * 4;
-	const uint8_t *src = reinterpret_cast<const uint8_t *>(t->output);
-	const bool direct = t->registered_out && argb_out >= (uint8_t *)t->registered_out &&
-	                    argb_out + row_bytes * t->height <= (uint8_t *)t->registered_out + t->registered_bytes;
-	uint8_t *land = direct ? argb_out : t->pinned_out;  // where the copies land; staged bands are memcpy'd as they arrive
-	volatile unsigned int *flags = t->host_flags;
-	int staged = 0;  // bands already moved from the staging buffer to the caller (staged path)
-	auto band_off = [&](int b) { return (size_t)b * band_rows * row_bytes; };
-	auto band_len = [&](int b) { return (size_t)std::min(band_rows, t->height - b * band_rows) * row_bytes; };
-	auto drain = [&](int issued, bool block) -> cudaError_t {
-		while (!direct && staged < issued) {
-			cudaError_t q = block ? cudaEventSynchronize(t->band_ev[staged]) : cudaEventQuery(t->band_ev[staged]);
-			if (q == cudaErrorNotReady) return cudaSuccess;
-			if (q != cudaSuccess) return q;
-			memcpy(argb_out + band_off(staged), t->pinned_out + band_off(staged), band_len(staged));
-			++staged;
-		}
-		return cudaSuccess;
-	};
-	bool kernel_done = false;
-	for (int b = 0; b < n_bands; ++b) {
-		unsigned spins = 0;
-		while (flags[b] != t->frame_epoch) {
-			__builtin_ia32_pause();
-			if (kernel_done) return fail(t, SRT_ERR_CUDA, "fused frame: the kernel ended without completing band %d", b);
-			if ((++spins & 127u) == 0) {
-				SRT_CUDA(t, drain(b, false));
-				cudaError_t q = cudaEventQuery(t->frame_ev);
-				if (q == cudaSuccess) kernel_done = true;  // one more look at the flag, then give up
-				else if (q != cudaErrorNotReady) return fail(t, SRT_ERR_CUDA, "fused frame failed: %s", cudaGetErrorString(q));
-			}
-		}
-		SRT_CUDA(t, cudaMemcpyAsync(land + band_off(b), src + band_off(b), band_len(b), cudaMemcpyDeviceToHost, t->copy_stream));
-		if (!direct) SRT_CUDA(t, cudaEventRecord(t->band_ev[b], t->copy_stream));
-	}
-	SRT_CUDA(t, drain(n_bands, true));
-	SRT_CUDA(t, cudaStreamSynchronize(t->copy_stream));
-	SRT_CUDA(t, cudaStreamSynchronize(t->stream));
-	t->frame_counters_dirty = false;
-	return SRT_OK;
-}
-
 int srt_render_frame(srt_tracer *t, const srt_render_data *rd, uint32_t ticks_stopped, uint8_t *argb_out) {
 	SRT_BIND(t);
 	if (!argb_out) return fail(t, SRT_ERR_INVALID, "output is null");
 	srt::RenderParams p{};
 	if (int rc = make_params(t, rd, p)) return rc;
-	// the fused pass needs a full frame with work in it; tile-sharded launches (srt_set_row_bands) and empty ones
-	// (render.cl:403: zero bounces add zero radiance) take the separate kernels
-	const bool can_fuse = t->band_n <= 1 && p.num_bounces > 0 && p.total_items > 0;
-	// The fused pass is opt-in (SRT_FRAME_FUSED): its in-kernel resolve costs the render kernel ~11 % (1080p, BASELINE
-	// config 2: +8.5 % instructions, a release increment per finished sample) and hides ~0.14 ms of resolve + read-back:
-	// measured against the separate steps it is +2..9 % at 1 spp, +-3 % at 2 spp, -2..-4 % from 4 spp up and on
-	// dense-sweep scenes -- within run-to-run noise where it wins, so AUTO does not pick it
-	const bool fused = can_fuse && t->frame_pipeline == SRT_FRAME_FUSED;
-	if (fused) return render_frame_fused(t, p, ticks_stopped, argb_out);
+	// launches restricted to row bands (tile sharding) and launches without work (render.cl:403: zero bounces add zero
+	// radiance) take the separate steps
+	const bool full_frame = t->band_n <= 1 && p.num_bounces > 0 && p.total_items > 0;
 	// a full frame into the page-locked caller vector: one epilogue kernel accumulates, resolves and stores the image
 	// into the caller's memory directly (no separate `average` launch, no copy-engine transfer after it)
 	const bool direct = t->registered_out && argb_out >= (uint8_t *)t->registered_out &&
 	                    argb_out + (size_t)t->width * t->height * 4 <= (uint8_t *)t->registered_out + t->registered_bytes;
-	if (t->frame_pipeline != SRT_FRAME_SEPARATE && can_fuse && direct && t->registered_dev && ((uintptr_t)argb_out & 15) == 0) {
+	if (t->frame_pipeline != SRT_FRAME_SEPARATE && full_frame && direct && t->registered_dev && ((uintptr_t)argb_out & 15) == 0) {
 		t->epilogue_host = reinterpret_cast<uchar4 *>(t->registered_dev + (argb_out - (uint8_t *)t->registered_out));
 		t->epilogue_steps = ticks_stopped;
 		const int rc = launch_params<false>(t, p);
@@ -836,7 +715,7 @@ int srt_render_frame(srt_tracer *t, const srt_render_data *rd, uint32_t ticks_st
 
 int srt_set_frame_pipeline(srt_tracer *t, int mode) {
 	if (!t) return SRT_ERR_INVALID;
-	if (mode != SRT_FRAME_AUTO && mode != SRT_FRAME_SEPARATE && mode != SRT_FRAME_FUSED)
+	if (mode != SRT_FRAME_AUTO && mode != SRT_FRAME_SEPARATE)
 		return fail(t, SRT_ERR_INVALID, "unknown frame pipeline %d", mode);
 	t->frame_pipeline = mode;
 	return SRT_OK;

@@ -122,7 +122,7 @@ class Tracer:
         self.scene_data = np.zeros(1, SCENE_DATA)
         if os.environ.get("SRT_SWEEP_FILTER"):  # test / tuning hook: "auto", "one", "two" (bit-identical results)
             self.set_sweep_filter(os.environ["SRT_SWEEP_FILTER"])
-        if os.environ.get("SRT_FRAME_PIPELINE"):  # test / tuning hook: "auto", "separate", "fused" (bit-identical results)
+        if os.environ.get("SRT_FRAME_PIPELINE"):  # test / tuning hook: "auto", "separate" (bit-identical results)
             self.set_frame_pipeline(os.environ["SRT_FRAME_PIPELINE"])
         if os.environ.get("SRT_SCHEDULE"):  # test / tuning hook: "auto", "plain", "wavefront" (bit-identical results)
             self.set_schedule(os.environ["SRT_SCHEDULE"])
@@ -213,9 +213,9 @@ class Tracer:
         self._check(self._lib.srt_set_schedule(self._h, {"auto": 0, "plain": 1, "wavefront": 2}[schedule]))
 
     def set_frame_pipeline(self, mode):
-        """srt_set_frame_pipeline: "auto" | "separate" | "fused" -- whether render() accumulates, resolves and reads back
-        inside the render kernel's own run (fused) or as separate steps after it."""
-        self._check(self._lib.srt_set_frame_pipeline(self._h, {"auto": 0, "separate": 1, "fused": 2}[mode]))
+        """srt_set_frame_pipeline: "auto" | "separate" -- whether render() into the pinned vector may run accumulate +
+        average + read-back as one epilogue kernel, or always takes the separate steps."""
+        self._check(self._lib.srt_set_frame_pipeline(self._h, {"auto": 0, "separate": 1}[mode]))
 
     def set_sweep_filter(self, mode):
         """srt_set_sweep_filter: "auto" | "one" | "two" -- which conservative filter precedes the exact triangle test."""
