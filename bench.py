@@ -508,7 +508,8 @@ def main():
             "gpu_launches": args.steps * 3,  # per step: render (16 launches batched) + accumulate + average
             "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "api": "Tracer.update_scene + clear_canvas + 16 x Tracer.render(ticks, host_output) per step, wall clock; "
-                           "the output vector is page-locked once with Tracer.pin_output"},
+                           "the output vector is page-locked once with Tracer.pin_output (render() then ends in one epilogue kernel that "
+                           "stores the image into it)"},
             "roofline": roofline, "cpu_baseline": cpu_baseline,
             "fp32_peak_measured_tflops": g.peak_tf, "sm_clock_est_mhz": getattr(g, "est_mhz", None),
             "configs": configs, "strong": strong, "mgpu_parity": mgpu_parity}))

@@ -173,14 +173,10 @@ __device__ __forceinline__ void tri_exact(const float4 v0, const float4 e1, cons
 // which covers both error terms (the det term three times over, so that a wrong sign of a near-zero det is
 // harmless too).  A triangle is dropped only when the reference's u test is certain to fail; NaNs compare false
 // and survive; every survivor runs tri_exact on the reference operands.
-// det and t = d . m are both dot products with d, so they are evaluated TOGETHER as one chain of packed FP32x2
-// operations (FMUL2, FFMA2, FFMA2: __fmul2_rn / __ffma2_rn, new on sm_100; each half is rounded exactly like the
-// scalar instruction, so nothing changes numerically): 10 instructions per pair instead of 13.  Packed instructions
-// issue to the fmaheavy sub-pipe only, so packing more than this (two triangles per operation was tried) idles
-// fmalite and gains nothing.  The record and the ray's shared-memory image are laid out for it: n' and m interleaved,
-// d stored twice.
 //   record (40 B): a = {n'.x, m.x}  b = {n'.y, m.y}  c = {n'.z, m.z}  e = {e2.x, e2.y}  f = {e2.z, g}
-//   ray (48 B): r0 = {d.x, d.x, d.y, d.y}  r1 = {d.z, d.z, c.x, c.y}  r2 = {c.z, o.x, o.y, o.z},  c = o x d
+// (n' and m interleaved: the layout of an earlier form of the sweep that evaluated {det, t} as one packed chain per ray;
+// the present form -- two RAYS per packed operation, tri_filter_sweep below -- reads every field as a scalar, so the
+// order is immaterial)
 struct TriFlt {
 	float2 a, b, c, e, f;
 };
@@ -232,7 +228,7 @@ __device__ __forceinline__ uint32_t tri_filter_sweep(const TriFlt &r, const floa
 // (oracle/filter_check.c checks this filter too: 1e8 adversarial pairs, no wrong reject).  Survivors: ~2 per real hit.
 //   record (80 B): q0 = {n'.x, n'.y, n'.z, g}  q1 = {-m.x, -m1.x, -m.y, -m1.y}  q2 = {-m.z, -m1.z, e2.x, e1.x}
 //                  q3 = {e2.y, e1.y, e2.z, e1.z}  (+16 B pad: the 80 B stride keeps the lanes' LDS.128 conflict-free)
-//   ray (64 B):    r0 = {d.x, d.x, d.y, d.y}  r1 = {d.z, d.z, c.x, c.x}  r2 = {c.y, c.y, c.z, c.z}  r3 = {o, -}
+// evaluated for two rays per packed operation like tri_filter_sweep (per ray, per half: det, -t, -t1 = d . (-m1), su, sv)
 struct TriUV {
 	float4 q0, q1, q2, q3;
 };
@@ -593,15 +589,16 @@ constexpr int RENDER_THREADS = SRT_RENDER_THREADS;
 //     mbarrier, TILE_STAGES tiles ahead of the consumer: no lane issues a global load for the sweep;
 //   * every lane lifts TRIS_PER_LANE triangles of the current tile into REGISTERS (40 B stride: conflict-free
 //     LDS.64), so all 32 lanes are busy however few rays are parked;
-//   * the parked rays (3 x float4 each: d duplicated for the packed FP32x2 chain, c = o x d, o; published once per
-//     phase) are broadcast two per trip; every lane runs tri_filter_sweep on its own triangles and one VOTE per
-//     triangle slot hands the 32-bit survivor mask to the ray's owner lane;
-//   * after a tile the owners expand their masks into a per-warp ring of (ray << 27 | triangle) PAIRS, and the ring
+//   * the parked rays publish their operands once per phase, two rays to a record (12 floats {A, B} x (d, c = o x d));
+//     a trip takes one record and every lane runs tri_filter_sweep for BOTH rays on its own triangles, in packed
+//     FP32x2 instructions whose halves are the two rays; a lane keeps, per triangle slot, the bit mask of the rays
+//     its triangle survived;
+//   * after a tile the lanes expand their masks into a per-warp ring of (ray << 27 | triangle) PAIRS, and the ring
 //     is drained 32 pairs at a time by ALL lanes: tri_exact on the reference operands (tri_hot, LDG.128 x 3 through
 //     L1/L2), folded into best[ray] by a shared-memory atomicMin on (t bits << 32 | triangle + 1), which keeps the
 //     closest hit and, on equal t, the lowest triangle index -- the order of the sequential loop, render.cl:324-350.
-// Shared-memory traffic is 48 B per ray per tile instead of 40 B per ray per triangle, which is what moves the loop
-// from the shared-memory crossbar limit to the issue limit.
+// Shared-memory traffic is 24 B per ray per tile instead of 40 B per ray per triangle; what bounds the loop is the FMA
+// pipe's register-operand bandwidth (scripts/microbench/fma_operands.cu).
 #ifndef SRT_TRIS_PER_LANE
 #define SRT_TRIS_PER_LANE 4
 #endif
@@ -762,9 +759,9 @@ __device__ SRT_PHASE_ATTR void triangle_phase(const DevScene &sc, int n, int tri
 				// sweep to land (and makes a one-stage ring sufficient)
 				__syncwarp();  // every lane has read this stage
 				if (lane == 0 && t + TILE_STAGES < ntiles) issue(t + TILE_STAGES);
-				// two parked rays per trip (the slots are dense: an odd count is padded with a null ray whose bit is masked
-				// off below).  A lane keeps, per triangle slot, the bit mask of the RAYS its triangle survived: one
-				// predicated OR per pair -- no vote, no hand-off to an owner lane.
+				// two parked rays per trip, evaluated TOGETHER (tri_filter_sweep: one packed operation serves both); the
+				// slots are dense, an odd count is padded with a null ray whose bit is masked off below.  A lane keeps,
+				// per triangle slot, the bit mask of the RAYS its triangle survived -- no vote, no hand-off to an owner lane.
 				const float4 *rp = reinterpret_cast<const float4 *>(pairbuf);
 				int sh = 0;
 				for (int i = 0; i < nrays; i += 2, rp += 3, sh += 2) {  // warp-uniform
