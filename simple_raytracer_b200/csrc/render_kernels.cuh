@@ -576,6 +576,9 @@ __device__ __forceinline__ void scatter(const DevScene &sc, int material, vec3 p
 #ifndef SRT_MIN_BLOCKS_ANALYTIC
 #define SRT_MIN_BLOCKS_ANALYTIC 7
 #endif
+#ifndef SRT_MIN_BLOCKS_WAVEFRONT  // wavefront schedule, scenes without models: 8 x 128 threads x 64 registers = the register file
+#define SRT_MIN_BLOCKS_WAVEFRONT 8
+#endif
 #ifndef SRT_MIN_BLOCKS_BVH
 #define SRT_MIN_BLOCKS_BVH 6
 #endif
@@ -912,8 +915,16 @@ constexpr int SKYQ_WORDS = 10;   // item, color.xyz, mask.xyz, d.xyz
 #define SRT_WAVEFRONT 1
 #endif
 constexpr int HITQ_WORDS = 16;   // item, seed, position.xyz, d.xyz, mask.xyz, color.xyz, shape << 8 | bounce, triangle
-constexpr int QUEUE_WARP_BYTES = (RAYQ_WORDS + SKYQ_WORDS + (SRT_WAVEFRONT ? HITQ_WORDS : 0)) * QUEUE_SLOTS * 4;
+constexpr int QUEUE_WARP_BYTES = (RAYQ_WORDS + SKYQ_WORDS) * QUEUE_SLOTS * 4;  // plain schedule: ray and sky rings
 constexpr int QUEUE_SMEM_BYTES = (SRT_RENDER_THREADS / 32) * QUEUE_WARP_BYTES;
+// wavefront schedule: a ONE-batch ray ring (see its refill step), the sky ring, and the hit ring -- whose triangle word
+// only the builds that know models carry.  Without it a warp needs 7040 bytes, and 8 CTAs x (4 x 7040 + 1024 reserved)
+// are exactly the 233472 bytes of shared memory an SM has: scenes without models run 8 CTAs (32 warps) per SM.
+constexpr int RAYQ_SLOTS = 32;
+__host__ __device__ constexpr int wavefront_warp_bytes(bool models) {
+	return (RAYQ_WORDS * RAYQ_SLOTS + SKYQ_WORDS * QUEUE_SLOTS + (models ? HITQ_WORDS : HITQ_WORDS - 1) * QUEUE_SLOTS) * 4;
+}
+__host__ __device__ constexpr int wavefront_smem_bytes(bool models) { return (SRT_RENDER_THREADS / 32) * wavefront_warp_bytes(models); }
 constexpr int BIG_SKYQ_BYTES = SRT_BIG_SKYQ ? (SRT_RENDER_THREADS / 32) * SKYQ_WORDS * QUEUE_SLOTS * 4 : 0;
 
 // MODE selects the build: MODE_ANALYTIC for scenes without any model shape (no triangle code at all),
@@ -945,8 +956,8 @@ __device__ __forceinline__ void render_wavefront(const RenderParams &p, const De
 	constexpr bool MODELS = MODE != MODE_ANALYTIC && MODE != MODE_ANALYTIC_CONST;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const unsigned lt_mask = (1u << lane) - 1u;
-	uint32_t *rayq = reinterpret_cast<uint32_t *>(smem_raw + warp * QUEUE_WARP_BYTES);
-	float *skyq = reinterpret_cast<float *>(rayq + RAYQ_WORDS * QUEUE_SLOTS);
+	uint32_t *rayq = reinterpret_cast<uint32_t *>(smem_raw + warp * wavefront_warp_bytes(MODELS));
+	float *skyq = reinterpret_cast<float *>(rayq + RAYQ_WORDS * RAYQ_SLOTS);
 	uint32_t *hitq = reinterpret_cast<uint32_t *>(skyq + SKYQ_WORDS * QUEUE_SLOTS);
 	int ray_head = 0, ray_count = 0, sky_head = 0, sky_count = 0, hit_head = 0, hit_count = 0;  // warp-uniform
 	bool exhausted = false;
@@ -1025,10 +1036,35 @@ __device__ __forceinline__ void render_wavefront(const RenderParams &p, const De
 		}
 
 		// -- 2. the other lanes take fresh camera rays (start_path, 32 at a time with every lane active)
+		// The ray ring holds ONE batch (32 slots): lanes first take what is left in it, and only when that runs out is a new
+		// batch of 32 generated -- into the then empty ring -- for the remaining lanes.  (Generating ahead of the pops, as
+		// the plain schedule does, needs 64 slots; the 640 bytes saved per warp are what lets 8 CTAs share an SM.)
 		const unsigned need = __ballot_sync(FULL, !has_ray);
 		if (need) {
 			const int want = __popc(need);
-			if (ray_count < want && !exhausted) {
+			int served = 0;  // needing lanes already given a ray, in lane order
+#pragma unroll 1
+			for (int pass = 0; pass < 2; ++pass) {
+				const int r = __popc(need & lt_mask) - served;
+				if (!has_ray && r >= 0 && r < ray_count) {
+					const int sl = (ray_head + r) & (RAYQ_SLOTS - 1);
+					item = rayq[0 * RAYQ_SLOTS + sl];
+					seed = rayq[1 * RAYQ_SLOTS + sl];
+					d = mk(__uint_as_float(rayq[2 * RAYQ_SLOTS + sl]), __uint_as_float(rayq[3 * RAYQ_SLOTS + sl]),
+					       __uint_as_float(rayq[4 * RAYQ_SLOTS + sl]));
+					o = cam_origin;
+					mask = mk(1, 1, 1);
+					color = mk(0, 0, 0);
+					bounce = 0;
+					has_ray = true;
+				}
+				const int popped = min(want - served, ray_count);
+				ray_head = (ray_head + popped) & (RAYQ_SLOTS - 1);
+				ray_count -= popped;
+				served += popped;
+				__syncwarp();
+				if (served == want || exhausted || pass == 1) break;
+				// the ring is empty: the next 32 work items (start_path with every lane active)
 				unsigned int base = 0;
 				if (lane == 0) {  // 64-bit cursor: stepping past the end can never wrap into the item range
 					const unsigned long long b = atomicAdd(cursor, 32ull);
@@ -1042,37 +1078,19 @@ __device__ __forceinline__ void render_wavefront(const RenderParams &p, const De
 					uint32_t sd;
 					vec3 oo, dd;
 					start_path(p, it, sd, oo, dd);
-					const int sl = (ray_head + ray_count + __popc(vm & lt_mask)) & (QUEUE_SLOTS - 1);
-					rayq[0 * QUEUE_SLOTS + sl] = it;
-					rayq[1 * QUEUE_SLOTS + sl] = sd;
-					rayq[2 * QUEUE_SLOTS + sl] = __float_as_uint(dd.x);
-					rayq[3 * QUEUE_SLOTS + sl] = __float_as_uint(dd.y);
-					rayq[4 * QUEUE_SLOTS + sl] = __float_as_uint(dd.z);
+					const int sl = __popc(vm & lt_mask);
+					rayq[0 * RAYQ_SLOTS + sl] = it;
+					rayq[1 * RAYQ_SLOTS + sl] = sd;
+					rayq[2 * RAYQ_SLOTS + sl] = __float_as_uint(dd.x);
+					rayq[3 * RAYQ_SLOTS + sl] = __float_as_uint(dd.y);
+					rayq[4 * RAYQ_SLOTS + sl] = __float_as_uint(dd.z);
 					if (COUNT) cnt.samples += 1;
 				}
-				ray_count += __popc(vm);
+				ray_head = 0;
+				ray_count = __popc(vm);
 				exhausted = vm != FULL;
 				__syncwarp();
 			}
-			if (!has_ray) {
-				const int r = __popc(need & lt_mask);
-				if (r < ray_count) {
-					const int sl = (ray_head + r) & (QUEUE_SLOTS - 1);
-					item = rayq[0 * QUEUE_SLOTS + sl];
-					seed = rayq[1 * QUEUE_SLOTS + sl];
-					d = mk(__uint_as_float(rayq[2 * QUEUE_SLOTS + sl]), __uint_as_float(rayq[3 * QUEUE_SLOTS + sl]),
-					       __uint_as_float(rayq[4 * QUEUE_SLOTS + sl]));
-					o = cam_origin;
-					mask = mk(1, 1, 1);
-					color = mk(0, 0, 0);
-					bounce = 0;
-					has_ray = true;
-				}
-			}
-			const int popped = min(want, ray_count);
-			ray_head = (ray_head + popped) & (QUEUE_SLOTS - 1);
-			ray_count -= popped;
-			__syncwarp();
 		}
 		const bool any_ray = __any_sync(FULL, has_ray);
 		if (!any_ray && hit_count > 0) continue;  // only queued hits are left: the next trip shades them
@@ -1127,7 +1145,10 @@ __device__ __forceinline__ void render_wavefront(const RenderParams &p, const De
 // hit until 32 are there only lengthens the ragged end (BASELINE config 1, 3 items per thread: +6 % plain) and for
 // launches whose bounce count does not fit the hit record's 8 bits.
 template <bool COUNT, int MODE, bool WF>
-__global__ void __launch_bounds__(RENDER_THREADS, MODE == MODE_BIG_MODELS ? SRT_MIN_BLOCKS : (MODE == MODE_BVH ? SRT_MIN_BLOCKS_BVH : SRT_MIN_BLOCKS_ANALYTIC))
+__global__ void __launch_bounds__(RENDER_THREADS, MODE == MODE_BIG_MODELS ? SRT_MIN_BLOCKS
+                                                  : MODE == MODE_BVH      ? SRT_MIN_BLOCKS_BVH
+                                                  : (WF && (MODE == MODE_ANALYTIC || MODE == MODE_ANALYTIC_CONST)) ? SRT_MIN_BLOCKS_WAVEFRONT
+                                                                                                                    : SRT_MIN_BLOCKS_ANALYTIC)
 render_kernel(const __grid_constant__ RenderParams p, const __grid_constant__ DevScene sc,
               const __grid_constant__ ShapeTable tab, float4 *__restrict__ scratch,
               unsigned long long *__restrict__ cursor, Counters *__restrict__ counters) {

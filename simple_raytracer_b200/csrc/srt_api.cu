@@ -224,7 +224,10 @@ int launch_render_impl(srt_tracer *t, const srt::RenderParams &p) {
 template <bool COUNT, int MODE, bool WF>
 int launch_render_impl(srt_tracer *t, const srt::RenderParams &p) {
 	auto kernel = srt::render_kernel<COUNT, MODE, WF>;
-	const int smem = MODE == srt::MODE_BIG_MODELS ? srt::RENDER_SMEM_BYTES + srt::BIG_SKYQ_BYTES : srt::QUEUE_SMEM_BYTES;
+	constexpr bool MODELS = MODE != srt::MODE_ANALYTIC && MODE != srt::MODE_ANALYTIC_CONST;
+	const int smem = MODE == srt::MODE_BIG_MODELS ? srt::RENDER_SMEM_BYTES + srt::BIG_SKYQ_BYTES
+	                 : WF                          ? srt::wavefront_smem_bytes(MODELS)
+	                                               : srt::QUEUE_SMEM_BYTES;
 	int &grid = t->render_grid[COUNT ? 1 : 0][MODE][WF ? 1 : 0];
 	if (grid == 0) {
 		int per_sm = 0;
