@@ -605,8 +605,8 @@ constexpr int RENDER_THREADS = SRT_RENDER_THREADS;
 #ifndef SRT_TRIS_PER_LANE
 #define SRT_TRIS_PER_LANE 4
 #endif
-#ifndef SRT_TILE_STAGES
-#define SRT_TILE_STAGES 1
+#ifndef SRT_TILE_STAGES  // mbarriers per warp = the most stages either record size gets out of the ring (see RING_BYTES)
+#define SRT_TILE_STAGES 2
 #endif
 constexpr int TRIS_PER_LANE = SRT_TRIS_PER_LANE;
 constexpr int TILE_TRIS = 32 * TRIS_PER_LANE;
@@ -626,7 +626,10 @@ constexpr int UV_BYTES = 80;
 constexpr int UV_MAX_TRIS = SRT_UV_MAX_TRIS;
 static_assert(TRIS_PER_LANE_UV <= TRIS_PER_LANE, "the survivor masks are sized for TRIS_PER_LANE slots");
 constexpr int TILE_BYTES = TILE_TRIS * FLT_BYTES > TILE_TRIS_UV * UV_BYTES ? TILE_TRIS * FLT_BYTES : TILE_TRIS_UV * UV_BYTES;
-constexpr int RING_BYTES = TILE_STAGES * TILE_BYTES;
+// The ring is ONE tile of the larger (two-strip, 80-byte) records = TWO tiles of the one-strip (40-byte) records: the
+// one-strip sweep runs two half-size stages, the two-strip sweep a single one (triangle_phase).
+constexpr int RING_BYTES = TILE_BYTES;
+static_assert(TILE_STAGES == 2 && 2 * TILE_TRIS * FLT_BYTES <= RING_BYTES && TILE_TRIS_UV * UV_BYTES <= RING_BYTES, "tile ring geometry");
 constexpr int RAYS_BYTES = 32 * 64;           // 32 rays x {origin, direction} (exact test) + 16 ray pairs x 12 floats (the filter)
 constexpr int PAIR_SLOTS = 256;               // ring of filter survivors (ray << 27 | triangle) awaiting the exact test
 constexpr int PAIRS_BYTES = PAIR_SLOTS * 4;
@@ -656,6 +659,19 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 	    "}\n" ::"r"(bar),
 	    "r"(parity)
 	    : "memory");
+}
+
+// Before shared memory that was just READ by ordinary loads is handed to an asynchronous bulk copy, the loads must have
+// completed -- issued is not enough: under shared-memory contention a load can still be queued when the copy's first
+// bytes land.  Two measures, both needed in principle and cheap in practice:
+//   * a real instruction chain that reads one destination register of EVERY load (an XOR folded three at a time by LOP3)
+//     and a store of its result: instructions issue in order and only when their operands are there, so everything after
+//     the store is issued after the data of every load has arrived;
+//   * fence.proxy.async, which orders this thread's generic-proxy accesses before later async-proxy ones.
+__device__ __forceinline__ uint32_t fbits(float x) { return __float_as_uint(x); }
+__device__ __forceinline__ void loads_done_before_async_copy(uint32_t acc, uint32_t *sink) {
+	*sink = acc;
+	asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
 // Exact test of one filter survivor by whichever lane picked it up: the reference arithmetic (tri_exact) on the
@@ -698,14 +714,18 @@ __device__ SRT_PHASE_ATTR void triangle_phase(const DevScene &sc, int n, int tri
 	                     : reinterpret_cast<const char *>(sc.tri_flt + 5 * (size_t)tri_begin);
 	const float4 *exact = sc.tri_hot + 3 * (size_t)tri_begin;  // survivors fetch the reference operands from L1/L2
 	const int ntiles = (n + tile_tris - 1) / tile_tris;
+	// One-strip records: two stages -- tile t + 1 is copied into the stage that held tile t - 1, whose registers the
+	// previous sweep has consumed to the last instruction, while tile t is being swept.  Two-strip records fill the
+	// ring with one tile, so the stage that is refilled is the one that was just lifted into registers, and the loads
+	// have to be known complete first (loads_done_before_async_copy).
+	constexpr int stages = uv ? 1 : 2;
 	auto issue = [&](int t) {
-		const int st = t % TILE_STAGES;
+		const int st = t % stages;
 		const uint32_t bytes = ((uint32_t)min(tile_tris, n - t * tile_tris) * rec_bytes + 15u) & ~15u;  // the arrays are padded
 		SRT_ASSERT(bytes > 0 && bytes <= (uint32_t)TILE_BYTES && ((size_t)(src + (size_t)t * tile_bytes) & 15) == 0);
-		bulk_load_tile(wsmem_s + st * TILE_BYTES, src + (size_t)t * tile_bytes, bytes, bars_s + st * 8);
+		bulk_load_tile(wsmem_s + st * tile_bytes, src + (size_t)t * tile_bytes, bytes, bars_s + st * 8);
 	};
-	if (lane == 0)
-		for (int t = 0; t < min(ntiles, TILE_STAGES); ++t) issue(t);
+	if (lane == 0) issue(0);  // always ONE tile ahead of the sweep
 	// the parked rays take DENSE slots 0 .. nrays-1 (slot = rank of the lane among the parked ones)
 	const unsigned ray_mask = __ballot_sync(FULL, active);
 	const int nrays = __popc(ray_mask);
@@ -714,6 +734,7 @@ __device__ SRT_PHASE_ATTR void triangle_phase(const DevScene &sc, int n, int tri
 	// the filter's operands, two rays to a record: 12 floats {A, B} x (d.x, d.y, d.z, c.x, c.y, c.z), c = o x d, for the
 	// rays in slots 2k and 2k + 1; and per ray its origin and direction for the exact test
 	float *pairbuf = reinterpret_cast<float *>(rays + 64);  // behind the 32 x 2 float4 of origins and directions
+	uint32_t *sink = reinterpret_cast<uint32_t *>(pairbuf + 16 * 12);  // 32 words behind the 16 pair records (loads_done_...)
 	if (active) {
 		const vec3 c = cross(o, d);
 		float *pr = pairbuf + 12 * (slot >> 1) + (slot & 1);
@@ -745,10 +766,10 @@ __device__ SRT_PHASE_ATTR void triangle_phase(const DevScene &sc, int n, int tri
 #pragma unroll
 		for (int q = 0; q < TRIS_PER_LANE; ++q) cand[q] = 0;
 		if (t < ntiles) {
-			const int st = t % TILE_STAGES;
+			const int st = t % stages;
 			mbar_wait(bars_s + st * 8, (parity >> st) & 1u);
 			parity ^= 1u << st;
-			const unsigned char *tile = tiles + st * TILE_BYTES;
+			const unsigned char *tile = tiles + st * tile_bytes;
 			if (!uv) {
 				// my triangles of this tile: slot q holds triangle q*32 + lane
 				TriFlt tf[TRIS_PER_LANE];
@@ -758,10 +779,10 @@ __device__ SRT_PHASE_ATTR void triangle_phase(const DevScene &sc, int n, int tri
 					tf[q].a = r[0], tf[q].b = r[1], tf[q].c = r[2], tf[q].e = r[3], tf[q].f = r[4];
 					tf[q].f.y = fma_(tf[q].f.y, rmax, 2e-6f * SRT_MARGIN_SCALE);  // g -> M
 				}
-				// the tile now lives in registers: its stage is refilled BEFORE the sweep, which gives the copy a whole
-				// sweep to land (and makes a one-stage ring sufficient)
-				__syncwarp();  // every lane has read this stage
-				if (lane == 0 && t + TILE_STAGES < ntiles) issue(t + TILE_STAGES);
+				// the tile now lives in registers; the NEXT tile goes into the other stage -- the one the previous sweep
+				// has finished with -- and has this whole sweep to land
+				__syncwarp();
+				if (lane == 0 && t + 1 < ntiles) issue(t + 1);
 				// two parked rays per trip, evaluated TOGETHER (tri_filter_sweep: one packed operation serves both); the
 				// slots are dense, an odd count is padded with a null ray whose bit is masked off below.  A lane keeps,
 				// per triangle slot, the bit mask of the RAYS its triangle survived -- no vote, no hand-off to an owner lane.
@@ -783,8 +804,17 @@ __device__ SRT_PHASE_ATTR void triangle_phase(const DevScene &sc, int n, int tri
 					tv[q].q0 = r[0], tv[q].q1 = r[1], tv[q].q2 = r[2], tv[q].q3 = r[3];
 					tv[q].q0.w = fma_(tv[q].q0.w, rmax, 2e-6f * SRT_MARGIN_SCALE);  // g -> M
 				}
+				// single stage: the next tile overwrites the one just lifted into registers, which has to be literally
+				// true first -- the loads above are only ISSUED at this point, and under shared-memory contention (16
+				// warps per SM lifting 10 KB each) a load can still be queued when the copy's first bytes land; the lane
+				// would then sweep a mixture of two tiles (seen as rare missed hits once the sweep got faster)
+				uint32_t acc = 0;
+#pragma unroll
+				for (int q = 0; q < TRIS_PER_LANE_UV; ++q)  // one register of each of the four loads of the record
+					acc ^= fbits(tv[q].q0.x) ^ fbits(tv[q].q1.x) ^ fbits(tv[q].q2.x) ^ fbits(tv[q].q3.x);
+				loads_done_before_async_copy(acc, sink + lane);
 				__syncwarp();
-				if (lane == 0 && t + TILE_STAGES < ntiles) issue(t + TILE_STAGES);
+				if (lane == 0 && t + 1 < ntiles) issue(t + 1);
 				const float4 *rp = reinterpret_cast<const float4 *>(pairbuf);
 				int sh = 0;
 				for (int i = 0; i < nrays; i += 2, rp += 3, sh += 2) {  // warp-uniform
