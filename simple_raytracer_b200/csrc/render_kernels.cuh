@@ -15,6 +15,7 @@
 #include <stdint.h>
 
 #include "device_math.cuh"
+#include "fastdiv.hpp"
 
 // Developer build with device-side invariant checks (compute-sanitizer is not available on the GPU pool):
 // scripts/build_variant.sh checks "-DSRT_DEBUG_CHECKS=1", then run the GPU tests with SRT_LIB pointing at it.
@@ -69,10 +70,34 @@ struct DevScene {
 // (7 shapes x ~20 instructions of loop overhead per bounce on BASELINE config 2).  finish_hit keeps reading the global
 // arrays: its index differs from lane to lane.
 constexpr int CONST_SHAPES = 16;
+// SRT_PAIR_SCAN: the wavefront build of such a scene scans the shapes TWO AT A TIME (scan_pairs below).  Consecutive
+// shapes of the same type form one "op" whose operands sit interleaved {A, B} in the table, so that every floating-point
+// operation before the per-shape decision is one packed FP32x2 instruction whose halves belong to shape A and shape B
+// (the ray operand is the broadcast scalar); a shape without a partner is an op whose B half repeats A and is ignored.
+#ifndef SRT_PAIR_SCAN
+#define SRT_PAIR_SCAN 1
+#endif
+#ifndef SRT_PAIR_UNROLL
+#define SRT_PAIR_UNROLL 1
+#endif
+constexpr int PAIR_UNROLL = SRT_PAIR_UNROLL;
+#ifndef SRT_PAIR_ANY  // scan_pairs: one combined miss test per sphere pair
+#define SRT_PAIR_ANY 1
+#endif
+#ifndef SRT_FASTDIV   // start_path: the item -> (launch, pixel, sample, row, column) divisions by precomputed multipliers
+#define SRT_FASTDIV 1
+#endif
 struct ShapeTable {
 	int4 hdr[CONST_SHAPES];
 	float4 a[CONST_SHAPES];
 	float4 b[CONST_SHAPES];
+#if SRT_PAIR_SCAN
+	int n_ops, pad_[3];
+	int4 op_hdr[CONST_SHAPES];   // {type, index of A, index of B or -1, -}
+	// spheres: {c.x A, c.x B, c.y A, c.y B} {c.z A, c.z B, -r*r A, -r*r B} {-}
+	// planes:  {p0.x A, p0.x B, p0.y A, p0.y B} {p0.z A, p0.z B, n.x A, n.x B} {n.y A, n.y B, n.z A, n.z B}
+	float4 op[CONST_SHAPES][3];
+#endif
 };
 
 // A kernel launch covers `num_launches` consecutive launches of the reference's kernel `render` that differ in
@@ -99,6 +124,10 @@ struct RenderParams {
 	unsigned int total_items;  // num_launches * items_per_launch: item = (launch * total_pixels + local_pixel) * num_samples + sample
 	float inv_ns;              // 1/num_samples when that is exact (num_samples a power of two), else 0
 	int uv_max_tris;           // models of at most this many triangles are swept with the two-strip filter
+#if SRT_FASTDIV
+	// n / d for ANY 32-bit n without a division (fastdiv.hpp): d = items_per_launch, num_samples, width
+	uint32_t dv_m[3], dv_s[3];
+#endif
 };
 
 struct Counters {
@@ -414,6 +443,76 @@ __device__ __forceinline__ int scan_shapes(const DevScene &sc, vec3 o, vec3 d, v
 	}
 	return -1;
 }
+
+#if SRT_PAIR_SCAN
+// closest_intersection (render.cl:293-378) for a scene of spheres and planes only, two shapes per trip of the loop.
+// Per half, every operation is the one scan_shapes performs for that shape, in the same order (L = c - o; the dot
+// products' FMUL, FFMA, FFMA; c = -r*r + L.L with the product rounded at upload by the same single multiplication;
+// b*b as a packed product whose halves feed two SCALAR adds -- ptxas contracts a packed multiply feeding a packed add
+// whatever --fmad says); the decisions are taken shape A first, then shape B, so hits replace each other in
+// array order exactly as in the sequential loop (strict `<`: the lower index wins a tie).  The loop runs for the whole
+// warp (a lane without a ray scans a dummy ray whose result is dropped), which makes the loop control, the table loads
+// and the type dispatch warp-uniform.
+__device__ __forceinline__ void sphere_decide(float disc, float b, int index, Hit &hit) {
+	if (disc >= 0.0f) {  // intersect_sphere, :190-203
+		float sq = sqrt_(disc);
+		float t = b - sq;
+		if (t < 0.0f) t = b + sq;
+		if (t >= 0.0f && t < hit.t) {
+			hit.t = t;
+			hit.shape = index;
+		}
+	}
+}
+__device__ __forceinline__ void plane_decide(float denom, float num, int index, Hit &hit) {
+	if (fabsf(denom) != 0.0f) {  // intersect_plane, :211-220
+		float t = div_(num, denom);
+		if (t >= 0.0f && t < hit.t) {
+			hit.t = t;
+			hit.shape = index;
+		}
+	}
+}
+__device__ __forceinline__ void scan_pairs(const ShapeTable &tab, vec3 o, vec3 d, Hit &hit) {
+	const float2 nox = make_float2(-o.x, -o.x), noy = make_float2(-o.y, -o.y), noz = make_float2(-o.z, -o.z);
+	const float2 dx = make_float2(d.x, d.x), dy = make_float2(d.y, d.y), dz = make_float2(d.z, d.z);
+	const int n_ops = tab.n_ops;
+#pragma unroll PAIR_UNROLL
+	for (int k = 0; k < n_ops; ++k) {
+		const int4 h = tab.op_hdr[k];
+		const float4 q0 = tab.op[k][0], q1 = tab.op[k][1];
+		// position - origin for both shapes (x - o is x + (-o) exactly)
+		const float2 Lx = __fadd2_rn(make_float2(q0.x, q0.y), nox), Ly = __fadd2_rn(make_float2(q0.z, q0.w), noy);
+		const float2 Lz = __fadd2_rn(make_float2(q1.x, q1.y), noz);
+		if (h.x == SHAPE_SPHERE) {
+			const float2 b = __ffma2_rn(Lz, dz, __ffma2_rn(Ly, dy, __fmul2_rn(Lx, dx)));   // dot(L, d)
+			const float2 ll = __ffma2_rn(Lz, Lz, __ffma2_rn(Ly, Ly, __fmul2_rn(Lx, Lx)));  // dot(L, L)
+			const float2 c = __fadd2_rn(make_float2(q1.z, q1.w), ll);                       // -r*r + dot(L, L), :187
+			const float2 bb = __fmul2_rn(b, b);
+			const float disc_a = __fadd_rn(bb.x, -c.x), disc_b = __fadd_rn(bb.y, -c.y);     // b*b - c, :188 (two roundings)
+			// (both square roots through one packed copy of sqrt's fast path, evaluated before the `disc >= 0` tests,
+			// measured 5 % SLOWER than this: most ray x sphere pairs miss, and a miss costs a compare and a branch here)
+#if SRT_PAIR_ANY
+			const bool ca = disc_a >= 0.0f, cb = h.z >= 0 && disc_b >= 0.0f;
+			if (ca || cb) {  // one test for the common case that the ray misses both
+				if (ca) sphere_decide(disc_a, b.x, h.y, hit);
+				if (cb) sphere_decide(disc_b, b.y, h.z, hit);
+			}
+#else
+			sphere_decide(disc_a, b.x, h.y, hit);
+			if (h.z >= 0) sphere_decide(disc_b, b.y, h.z, hit);
+#endif
+		} else {
+			const float4 q2 = tab.op[k][2];
+			const float2 nx = make_float2(q1.z, q1.w), ny = make_float2(q2.x, q2.y), nz = make_float2(q2.z, q2.w);
+			const float2 denom = __ffma2_rn(nz, dz, __ffma2_rn(ny, dy, __fmul2_rn(nx, dx)));  // dot(n, d)
+			const float2 num = __ffma2_rn(nz, Lz, __ffma2_rn(ny, Ly, __fmul2_rn(nx, Lx)));    // dot(n, p0 - o)
+			plane_decide(denom.x, num.x, h.y, hit);
+			if (h.z >= 0) plane_decide(denom.y, num.y, h.z, hit);
+		}
+	}
+}
+#endif
 
 // Position and shading normal of the winning hit (render.cl:311-312, :337-343, :361-362) followed by
 // the front-face flip (:372-375).
@@ -913,12 +1012,22 @@ __device__ __forceinline__ uchar4 argb_pixel(float4 c, float steps) {
 }
 // Start the camera path of work item `item` = local_pixel * num_samples + sample (render.cl:488-516).
 __device__ __forceinline__ void start_path(const RenderParams &p, unsigned int item, uint32_t &seed, vec3 &o, vec3 &d) {
+#if SRT_FASTDIV
+	const unsigned int launch = p.num_launches > 1 ? fast_div(item, p.dv_m[0], p.dv_s[0]) : 0u;
+#else
 	const unsigned int launch = p.num_launches > 1 ? item / p.items_per_launch : 0u;
+#endif
 	const unsigned int in_launch = item - launch * p.items_per_launch;
 	SRT_ASSERT(launch < (unsigned)p.num_launches && launch < (unsigned)MAX_BATCH && item < p.total_items);
+#if SRT_FASTDIV
+	const unsigned int lp = fast_div(in_launch, p.dv_m[1], p.dv_s[1]);  // local pixel
+	const unsigned int sample = in_launch - lp * (unsigned)p.num_samples;
+	const int row = (int)fast_div(lp, p.dv_m[2], p.dv_s[2]);
+#else
 	const unsigned int lp = in_launch / (unsigned)p.num_samples;  // local pixel
 	const unsigned int sample = in_launch - lp * (unsigned)p.num_samples;
 	const int row = (int)(lp / (unsigned)p.width);
+#endif
 	const int gx = (int)(lp - (unsigned)row * (unsigned)p.width);
 	const int gy = p.band_n > 1 ? ((row / p.band_h) * p.band_n + p.band_i) * p.band_h + (row % p.band_h) : row;
 	const uint32_t pix = (uint32_t)gx + (uint32_t)gy * (uint32_t)p.width;
@@ -1129,6 +1238,12 @@ __device__ __forceinline__ void render_wavefront(const RenderParams &p, const De
 
 		// -- 3. closest_intersection for every ray of the trip, :293-378
 		Hit hit = {__int_as_float(0x7f800000), -1, -1};
+#if SRT_PAIR_SCAN
+		if (MODE == MODE_ANALYTIC_CONST) {  // two shapes per packed operation, every lane (scan_pairs)
+			if (COUNT && has_ray) cnt.bounces += 1;
+			scan_pairs(tab, o, d, hit);
+		} else
+#endif
 		if (has_ray) {
 			if (COUNT) cnt.bounces += 1;
 			const vec3 inv = MODELS ? mk(rcp_(d.x), rcp_(d.y), rcp_(d.z)) : mk(0, 0, 0);

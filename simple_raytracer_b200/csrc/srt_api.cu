@@ -203,6 +203,13 @@ int make_params(srt_tracer *t, const srt_render_data *rd, srt::RenderParams &p) 
 		return fail(t, SRT_ERR_INVALID, "width*height*num_samples exceeds %llu work items per launch", srt::MAX_ITEMS);
 	p.items_per_launch = p.total_pixels * (unsigned int)rd->num_samples;
 	p.total_items = p.items_per_launch;
+#if SRT_FASTDIV
+	const uint32_t divisors[3] = {p.items_per_launch, (uint32_t)rd->num_samples, (uint32_t)rd->width};
+	for (int k = 0; k < 3; ++k) {
+		const srt::FastDiv fd = srt::fast_div_make(divisors[k]);
+		p.dv_m[k] = fd.m, p.dv_s[k] = fd.s;
+	}
+#endif
 	return SRT_OK;
 }
 
@@ -516,6 +523,32 @@ int srt_upload_scene(srt_tracer *t, const srt_shape *shapes, size_t n_shapes, co
 	t->shape_table = srt::ShapeTable{};
 	for (size_t i = 0; i < std::min<size_t>(n_shapes, srt::CONST_SHAPES); ++i)
 		t->shape_table.hdr[i] = hdr[i], t->shape_table.a[i] = a[i], t->shape_table.b[i] = b[i];
+#if SRT_PAIR_SCAN
+	if (!t->has_models && n_shapes <= (size_t)srt::CONST_SHAPES) {  // the ops of scan_pairs: neighbours of one type, two at a time
+		srt::ShapeTable &tab = t->shape_table;
+		int n_ops = 0;
+		for (size_t i = 0; i < n_shapes; ++n_ops) {
+			const bool pair = i + 1 < n_shapes && hdr[i + 1].x == hdr[i].x;
+			const size_t j = pair ? i + 1 : i;  // a single shape: the B half repeats A and is ignored
+			tab.op_hdr[n_ops] = make_int4(hdr[i].x, (int)i, pair ? (int)j : -1, 0);
+			if (hdr[i].x == SRT_SHAPE_SPHERE) {
+				// -r*r: ONE correctly rounded single-precision product, the operation cfma_(-r, r, .) starts with (this
+				// translation unit's host code is compiled with -ffp-contract=off, x86-64 SSE arithmetic)
+				const volatile float ra = a[i].w, rb = a[j].w;
+				const volatile float nra = -ra * ra, nrb = -rb * rb;
+				tab.op[n_ops][0] = make_float4(a[i].x, a[j].x, a[i].y, a[j].y);
+				tab.op[n_ops][1] = make_float4(a[i].z, a[j].z, nra, nrb);
+				tab.op[n_ops][2] = make_float4(0, 0, 0, 0);
+			} else {
+				tab.op[n_ops][0] = make_float4(a[i].x, a[j].x, a[i].y, a[j].y);
+				tab.op[n_ops][1] = make_float4(a[i].z, a[j].z, b[i].x, b[j].x);
+				tab.op[n_ops][2] = make_float4(b[i].y, b[j].y, b[i].z, b[j].z);
+			}
+			i = j + 1;
+		}
+		tab.n_ops = n_ops;
+	}
+#endif
 	t->bvh_ready = false;
 	t->have_scene = true;
 	if (t->accel == SRT_ACCEL_BVH) return build_bvh(t);
