@@ -77,10 +77,6 @@ constexpr int CONST_SHAPES = 16;
 #ifndef SRT_PAIR_SCAN
 #define SRT_PAIR_SCAN 1
 #endif
-#ifndef SRT_PAIR_UNROLL
-#define SRT_PAIR_UNROLL 1
-#endif
-constexpr int PAIR_UNROLL = SRT_PAIR_UNROLL;
 #ifndef SRT_PAIR_ANY  // scan_pairs: one combined miss test per sphere pair
 #define SRT_PAIR_ANY 1
 #endif
@@ -477,7 +473,7 @@ __device__ __forceinline__ void scan_pairs(const ShapeTable &tab, vec3 o, vec3 d
 	const float2 nox = make_float2(-o.x, -o.x), noy = make_float2(-o.y, -o.y), noz = make_float2(-o.z, -o.z);
 	const float2 dx = make_float2(d.x, d.x), dy = make_float2(d.y, d.y), dz = make_float2(d.z, d.z);
 	const int n_ops = tab.n_ops;
-#pragma unroll PAIR_UNROLL
+#pragma unroll 1  // (unrolled by two: 1 % slower)
 	for (int k = 0; k < n_ops; ++k) {
 		const int4 h = tab.op_hdr[k];
 		const float4 q0 = tab.op[k][0], q1 = tab.op[k][1];
@@ -1771,6 +1767,32 @@ __global__ void math_kernel(int op, const float *__restrict__ x, const float *__
 	case 7: r = log_x2(make_float2(x[i], y[i])).y; break;
 	case 8: r = cos_x2(make_float2(x[i], y[i])).x; break;
 	case 9: r = cos_x2(make_float2(x[i], y[i])).y; break;
+	case 10: r = rcp_sqrt_(x[i]); break;
+	case 11: r = rcp_(sqrt_(x[i])); break;
+	case 12: r = sqrt_x2(make_float2(x[i], y[i])).x; break;
+	case 13: r = sqrt_x2(make_float2(x[i], y[i])).y; break;
+	// EXHAUSTIVE checks: thread i compares the two forms on the bit patterns i * 2^32 / n ... (n = 2^20 threads cover all
+	// 2^32); the result is the number of patterns on which they differ (NaN payloads aside)
+	case 14:
+	case 15: {
+		const uint32_t span = (uint32_t)(0x100000000ull / n);
+		uint32_t bad = 0;
+		for (uint32_t k = 0; k < span; ++k) {
+			const float v = __uint_as_float((uint32_t)i * span + k);
+			float a, b;
+			if (op == 14) {
+				a = rcp_sqrt_(v), b = rcp_(sqrt_(v));
+			} else {
+				const float w = __uint_as_float(((uint32_t)i * span + k) * 2654435761u);  // some other pattern in the other half
+				const float2 p2 = sqrt_x2(make_float2(v, w));
+				a = p2.x, b = sqrt_(v);
+				if (!(__float_as_uint(p2.y) == __float_as_uint(sqrt_(w)) || (p2.y != p2.y && w != w) || (p2.y != p2.y && sqrt_(w) != sqrt_(w)))) ++bad;
+			}
+			if (!(__float_as_uint(a) == __float_as_uint(b) || (a != a && b != b))) ++bad;
+		}
+		r = (float)bad;
+		break;
+	}
 	}
 	out[i] = r;
 }

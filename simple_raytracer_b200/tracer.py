@@ -102,7 +102,9 @@ class _CudaView:
 
 class Tracer:
     MATH_OPS = {"log": 0, "cos": 1, "atan2pi": 2, "pow": 3, "sqrt": 4, "schlick": 5,
-                "log_x2_lo": 6, "log_x2_hi": 7, "cos_x2_lo": 8, "cos_x2_hi": 9}
+                "log_x2_lo": 6, "log_x2_hi": 7, "cos_x2_lo": 8, "cos_x2_hi": 9,
+                "rcp_sqrt": 10, "rcp_of_sqrt": 11, "sqrt_x2_lo": 12, "sqrt_x2_hi": 13,
+                "rcp_sqrt_all_patterns": 14, "sqrt_x2_all_patterns": 15}
 
     def __init__(self, width, height, skybox, device=-1):
         self._lib = load_library()
