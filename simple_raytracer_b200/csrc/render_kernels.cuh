@@ -77,6 +77,9 @@ constexpr int CONST_SHAPES = 16;
 #ifndef SRT_PAIR_SCAN
 #define SRT_PAIR_SCAN 1
 #endif
+#ifndef SRT_WF_CARRY  // render_wavefront: path-state registers carried across trips instead of re-initialised
+#define SRT_WF_CARRY 1
+#endif
 #ifndef SRT_PAIR_ANY  // scan_pairs: one combined miss test per sphere pair
 #define SRT_PAIR_ANY 1
 #endif
@@ -1114,12 +1117,23 @@ __device__ __forceinline__ void render_wavefront(const RenderParams &p, const De
 		__syncwarp();
 	};
 
+#if SRT_WF_CARRY
+	// Path state of the trip.  Declared OUTSIDE the loop: a lane without a ray keeps whatever its last path left here
+	// (every use is guarded by has_ray; the scan of a stale ray is computed and dropped), which saves re-creating
+	// fifteen defaults at the top of every trip.
+	unsigned int item = 0;
+	int bounce = 0;
+	uint32_t seed = 0;
+	vec3 o = mk(0, 0, 0), d = mk(0, 0, 1), mask = mk(1, 1, 1), color = mk(0, 0, 0);
+#endif
 	for (;;) {
 		bool has_ray = false;
+#if !SRT_WF_CARRY
 		unsigned int item = 0;
 		int bounce = 0;
 		uint32_t seed = 0;
 		vec3 o = mk(0, 0, 0), d = mk(0, 0, 1), mask = mk(1, 1, 1), color = mk(0, 0, 0);
+#endif
 
 		// -- 1. shade 32 queued hits (fewer only when no fresh ray is left to wait for)
 		const bool dry = exhausted && ray_count == 0;
