@@ -60,8 +60,11 @@ for c in (2, 3, 5):
         "capture": (f"profiles/{rnd}_ncu_c{c}_key_metrics.txt (ncu --set full --clock-control none; "
                     + ("one 16-launch srt_render_batch kernel + its accumulate_kernel, as bench.py's timed step runs them"
                        if c == 2 else f"one render_kernel launch of scripts/profile_target.py {c}, num_samples 4") + ")")}
-if traffic:
-    json.dump(traffic, open(os.path.join(P, "roofline_traffic.json"), "w"), indent=1)
+if traffic:  # configs without a fresh capture keep their entries
+    tj = os.path.join(P, "roofline_traffic.json")
+    merged = json.load(open(tj)) if os.path.exists(tj) else {}
+    merged.update(traffic)
+    json.dump(merged, open(tj, "w"), indent=1)
 
 for f in (f"{rnd}_bench.json", f"{rnd}_bench_reference.json", f"{rnd}_bench_launches.csv", f"{rnd}_environment.txt",
           f"{rnd}_pytest_gpu.log", f"{rnd}_fma_operands.txt", f"{rnd}_variants.txt"):
