@@ -77,6 +77,9 @@ constexpr int CONST_SHAPES = 16;
 #ifndef SRT_PAIR_SCAN
 #define SRT_PAIR_SCAN 1
 #endif
+#ifndef SRT_RING_V4   // render_wavefront: hit and sky records through 16-byte shared-memory accesses
+#define SRT_RING_V4 1
+#endif
 #ifndef SRT_WF_CARRY  // render_wavefront: path-state registers carried across trips instead of re-initialised
 #define SRT_WF_CARRY 1
 #endif
@@ -1097,6 +1100,15 @@ __device__ __forceinline__ void render_wavefront(const RenderParams &p, const De
 	uint32_t *rayq = reinterpret_cast<uint32_t *>(smem_raw + warp * wavefront_warp_bytes(MODELS));
 	float *skyq = reinterpret_cast<float *>(rayq + RAYQ_WORDS * RAYQ_SLOTS);
 	uint32_t *hitq = reinterpret_cast<uint32_t *>(skyq + SKYQ_WORDS * QUEUE_SLOTS);
+#if SRT_RING_V4
+	// Same rings, same bytes, but twelve of a hit record's words and eight of a sky record's travel as 16-byte vectors
+	// (slot-major float4 arrays: consecutive slots are 16 bytes apart, conflict-free LDS.128 / STS.128); the remaining
+	// words stay word arrays behind them.
+	//   hit4[0] = {pos.xyz, item}  hit4[1] = {d.xyz, seed}  hit4[2] = {mask.xyz, color.z}   words 12 .. 14 (15): color.xy, shape | bounce
+	//   sky4[0] = {color.xyz, item}  sky4[1] = {mask.xyz, d.z}                            words 8, 9: d.xy
+	float4 *hit4 = reinterpret_cast<float4 *>(hitq);
+	float4 *sky4 = reinterpret_cast<float4 *>(skyq);
+#endif
 	int ray_head = 0, ray_count = 0, sky_head = 0, sky_count = 0, hit_head = 0, hit_count = 0;  // warp-uniform
 	bool exhausted = false;
 	const vec3 cam_origin = mk(p.c2w[12], p.c2w[13], p.c2w[14]);
@@ -1104,10 +1116,18 @@ __device__ __forceinline__ void render_wavefront(const RenderParams &p, const De
 		unsigned int it = 0;
 		if (lane < n) {
 			const int sl = (sky_head + lane) & (QUEUE_SLOTS - 1);
+#if SRT_RING_V4
+			const float4 s0 = sky4[0 * QUEUE_SLOTS + sl], s1 = sky4[1 * QUEUE_SLOTS + sl];
+			it = __float_as_uint(s0.w);
+			const vec3 c = mk(s0.x, s0.y, s0.z);
+			vec3 m = mk(s1.x, s1.y, s1.z);
+			const vec3 dir = mk(skyq[8 * QUEUE_SLOTS + sl], skyq[9 * QUEUE_SLOTS + sl], s1.w);
+#else
 			it = __float_as_uint(skyq[0 * QUEUE_SLOTS + sl]);
 			const vec3 c = mk(skyq[1 * QUEUE_SLOTS + sl], skyq[2 * QUEUE_SLOTS + sl], skyq[3 * QUEUE_SLOTS + sl]);
 			vec3 m = mk(skyq[4 * QUEUE_SLOTS + sl], skyq[5 * QUEUE_SLOTS + sl], skyq[6 * QUEUE_SLOTS + sl]);
 			const vec3 dir = mk(skyq[7 * QUEUE_SLOTS + sl], skyq[8 * QUEUE_SLOTS + sl], skyq[9 * QUEUE_SLOTS + sl]);
+#endif
 			m = m * sky_box(sc, dir);
 			const vec3 r = c + m;
 			scratch[it] = make_float4(r.x, r.y, r.z, 0.f);
@@ -1141,6 +1161,15 @@ __device__ __forceinline__ void render_wavefront(const RenderParams &p, const De
 			const int n = min(hit_count, 32);
 			if (lane < n) {
 				const int sl = (hit_head + lane) & (QUEUE_SLOTS - 1);
+#if SRT_RING_V4
+				const float4 h0 = hit4[0 * QUEUE_SLOTS + sl], h1 = hit4[1 * QUEUE_SLOTS + sl], h2 = hit4[2 * QUEUE_SLOTS + sl];
+				const vec3 pos = mk(h0.x, h0.y, h0.z);
+				item = __float_as_uint(h0.w);
+				d = mk(h1.x, h1.y, h1.z);
+				seed = __float_as_uint(h1.w);
+				mask = mk(h2.x, h2.y, h2.z);
+				color = mk(__uint_as_float(hitq[12 * QUEUE_SLOTS + sl]), __uint_as_float(hitq[13 * QUEUE_SLOTS + sl]), h2.w);
+#else
 				item = hitq[0 * QUEUE_SLOTS + sl];
 				seed = hitq[1 * QUEUE_SLOTS + sl];
 				const vec3 pos = mk(__uint_as_float(hitq[2 * QUEUE_SLOTS + sl]), __uint_as_float(hitq[3 * QUEUE_SLOTS + sl]),
@@ -1151,6 +1180,7 @@ __device__ __forceinline__ void render_wavefront(const RenderParams &p, const De
 				          __uint_as_float(hitq[10 * QUEUE_SLOTS + sl]));
 				color = mk(__uint_as_float(hitq[11 * QUEUE_SLOTS + sl]), __uint_as_float(hitq[12 * QUEUE_SLOTS + sl]),
 				           __uint_as_float(hitq[13 * QUEUE_SLOTS + sl]));
+#endif
 				const uint32_t sb = hitq[14 * QUEUE_SLOTS + sl];
 				Hit hit = {0.f, (int)(sb >> 8), MODELS ? (int)hitq[15 * QUEUE_SLOTS + sl] : -1};
 				bounce = (int)(sb & 255u);
@@ -1266,6 +1296,13 @@ __device__ __forceinline__ void render_wavefront(const RenderParams &p, const De
 		if (is_hit) {
 			const vec3 pos = cfma3(d, hit.t, o);
 			const int sl = (hit_head + hit_count + __popc(hm & lt_mask)) & (QUEUE_SLOTS - 1);
+#if SRT_RING_V4
+			hit4[0 * QUEUE_SLOTS + sl] = make_float4(pos.x, pos.y, pos.z, __uint_as_float(item));
+			hit4[1 * QUEUE_SLOTS + sl] = make_float4(d.x, d.y, d.z, __uint_as_float(seed));
+			hit4[2 * QUEUE_SLOTS + sl] = make_float4(mask.x, mask.y, mask.z, color.z);
+			hitq[12 * QUEUE_SLOTS + sl] = __float_as_uint(color.x);
+			hitq[13 * QUEUE_SLOTS + sl] = __float_as_uint(color.y);
+#else
 			hitq[0 * QUEUE_SLOTS + sl] = item;
 			hitq[1 * QUEUE_SLOTS + sl] = seed;
 			hitq[2 * QUEUE_SLOTS + sl] = __float_as_uint(pos.x), hitq[3 * QUEUE_SLOTS + sl] = __float_as_uint(pos.y);
@@ -1276,16 +1313,24 @@ __device__ __forceinline__ void render_wavefront(const RenderParams &p, const De
 			hitq[10 * QUEUE_SLOTS + sl] = __float_as_uint(mask.z);
 			hitq[11 * QUEUE_SLOTS + sl] = __float_as_uint(color.x), hitq[12 * QUEUE_SLOTS + sl] = __float_as_uint(color.y);
 			hitq[13 * QUEUE_SLOTS + sl] = __float_as_uint(color.z);
+#endif
 			hitq[14 * QUEUE_SLOTS + sl] = ((uint32_t)hit.shape << 8) | (uint32_t)bounce;
 			if (MODELS) hitq[15 * QUEUE_SLOTS + sl] = (uint32_t)hit.tri;
 		}
 		if (is_miss) {
 			if (COUNT) cnt.sky += 1;
 			const int sl = (sky_head + sky_count + __popc(sm & lt_mask)) & (QUEUE_SLOTS - 1);
+#if SRT_RING_V4
+			sky4[0 * QUEUE_SLOTS + sl] = make_float4(color.x, color.y, color.z, __uint_as_float(item));
+			sky4[1 * QUEUE_SLOTS + sl] = make_float4(mask.x, mask.y, mask.z, d.z);
+			skyq[8 * QUEUE_SLOTS + sl] = d.x;
+			skyq[9 * QUEUE_SLOTS + sl] = d.y;
+#else
 			skyq[0 * QUEUE_SLOTS + sl] = __uint_as_float(item);
 			skyq[1 * QUEUE_SLOTS + sl] = color.x, skyq[2 * QUEUE_SLOTS + sl] = color.y, skyq[3 * QUEUE_SLOTS + sl] = color.z;
 			skyq[4 * QUEUE_SLOTS + sl] = mask.x, skyq[5 * QUEUE_SLOTS + sl] = mask.y, skyq[6 * QUEUE_SLOTS + sl] = mask.z;
 			skyq[7 * QUEUE_SLOTS + sl] = d.x, skyq[8 * QUEUE_SLOTS + sl] = d.y, skyq[9 * QUEUE_SLOTS + sl] = d.z;
+#endif
 		}
 		hit_count += __popc(hm);
 		sky_count += __popc(sm);
