@@ -196,7 +196,10 @@ int srt_debug_primary(srt_tracer *t, const srt_render_data *rd, int32_t *shape_i
 /* Same as srt_render, with the work counters of that launch added into *counters (slower). */
 int srt_render_counted(srt_tracer *t, const srt_render_data *rd, srt_counters *counters);
 /* Device math self-test: op 0 log, 1 cos, 2 atan2pi(x,y), 3 pow(x,y), 4 sqrt, 5 schlick(mu=x,cos=y); 6 / 7 = the two
- * halves of the packed-FP32x2 log of the pair {x, y}, 8 / 9 = of the packed cos (must equal ops 0 / 1 on x and on y). */
+ * halves of the packed-FP32x2 log of the pair {x, y}, 8 / 9 = of the packed cos (must equal ops 0 / 1 on x and on y);
+ * 10 = normalize's range-tested 1 / sqrt(x), 11 = the two correctly rounded intrinsics it stands in for; 12 / 13 = the
+ * halves of the packed sqrt of {x, y}; 14 / 15 = EXHAUSTIVE checks of ops 10 and 12 / 13 against the intrinsics: with
+ * n = 2^20, thread i compares them on the 4096 bit patterns from i * 4096 and returns the number of mismatches. */
 int srt_debug_math(srt_tracer *t, int op, const float *x, const float *y, float *out, size_t n);
 /* FP32 FMA-chain micro-benchmark on the handle's device: achieved TFLOP/s. */
 int srt_measure_fp32_peak(srt_tracer *t, double *tflops, double *sm_clock_mhz_est);
