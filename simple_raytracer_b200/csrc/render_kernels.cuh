@@ -1048,14 +1048,15 @@ __device__ __forceinline__ void start_path(const RenderParams &p, unsigned int i
 #endif
 constexpr int QUEUE_SLOTS = 64;  // < 32 left over + <= 32 pushed per trip
 constexpr int RAYQ_WORDS = 5;    // item, seed, d.xyz          (origin = camera position)
-constexpr int SKYQ_WORDS = 10;   // item, color.xyz, mask.xyz, d.xyz
+constexpr int SKYQ_WORDS = 10;   // item, color.xyz, mask.xyz, d.xyz   (wavefront schedule: grouped into two float4 + two words, SRT_RING_V4)
 // Wavefront schedule of the queue builds (SRT_WAVEFRONT, render_wavefront): hits go through a third ring, so that hit
 // shading -- 60 % of the instructions of an analytic scene -- always runs with 32 lanes instead of the ~25 whose ray hit
 // something in that trip.
 #ifndef SRT_WAVEFRONT
 #define SRT_WAVEFRONT 1
 #endif
-constexpr int HITQ_WORDS = 16;   // item, seed, position.xyz, d.xyz, mask.xyz, color.xyz, shape << 8 | bounce, triangle
+constexpr int HITQ_WORDS = 16;   // item, seed, position.xyz, d.xyz, mask.xyz, color.xyz, shape << 8 | bounce, triangle (grouped into three
+                                 // float4 + three / four words under SRT_RING_V4: render_wavefront)
 constexpr int QUEUE_WARP_BYTES = (RAYQ_WORDS + SKYQ_WORDS) * QUEUE_SLOTS * 4;  // plain schedule: ray and sky rings
 constexpr int QUEUE_SMEM_BYTES = (SRT_RENDER_THREADS / 32) * QUEUE_WARP_BYTES;
 // wavefront schedule: a ONE-batch ray ring (see its refill step), the sky ring, and the hit ring -- whose triangle word
