@@ -1341,6 +1341,8 @@ __device__ __forceinline__ void render_wavefront(const RenderParams &p, const De
 	}
 }
 
+// the three by-value kernel parameters + three pointers stay inside the 4 KB every CUDA kernel may take
+static_assert(sizeof(RenderParams) + sizeof(DevScene) + sizeof(ShapeTable) + 3 * sizeof(void *) <= 4096, "kernel parameter space");
 // WF: the queue builds exist with both schedules -- wavefront (hits shaded 32 at a time through the hit ring) for
 // launches that keep every thread busy for many items, plain (hits shaded in place) for short ones, where queueing a
 // hit until 32 are there only lengthens the ragged end (BASELINE config 1, 3 items per thread: +6 % plain) and for
